@@ -1,0 +1,106 @@
+"""GPU selection for worker processes + array/tensor classification helpers.
+
+The reference pins nothing: every spawned (t, c) worker targets ``cuda:0``
+(reference biahub/virtual_stain.py:323-335) and ``DeskewSettings.device`` defaults to ``"cpu"``
+(reference biahub/settings.py:356).  This package always computes on a B200, so a ``device``
+argument only selects WHICH GPU:
+
+* ``"cuda:K"``  → GPU K;  ``"cuda"`` → the per-process default below
+* ``"cpu"`` / ``None`` → the per-process default below (there is no CPU path to fall back to;
+  if no GPU is present the call raises)
+* env ``BIAHUB_B200_DEVICE`` (``"K"`` or ``"cuda:K"``) overrides everything.
+
+Per-process default: ``LOCAL_RANK`` if set (torchrun / one process per GPU), else
+``SLURM_LOCALID``, else ``os.getpid() % device_count`` so that the spawn-ed pool workers of
+``process_single_position`` spread over the GPUs of a node.
+"""
+
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+from . import _cabi
+
+_default_device = None
+
+
+def default_device() -> int:
+    global _default_device
+    if _default_device is None:
+        n = _cabi.device_count()
+        if n <= 0:
+            _cabi.require_device(0)  # raises with the library's message
+        for var in ("LOCAL_RANK", "SLURM_LOCALID"):
+            v = os.environ.get(var)
+            if v is not None and v.isdigit():
+                _default_device = int(v) % n
+                break
+        else:
+            _default_device = os.getpid() % n
+    return _default_device
+
+
+def resolve_device(device=None) -> int:
+    env = os.environ.get("BIAHUB_B200_DEVICE")
+    if env:
+        device = env
+    if device is None:
+        return default_device()
+    if isinstance(device, int):
+        return device
+    name = str(device)
+    if name.isdigit():
+        return int(name)
+    if name.startswith("cuda"):
+        if ":" in name:
+            return int(name.split(":", 1)[1])
+        return default_device()
+    if name == "cpu":
+        return default_device()
+    raise ValueError(f"unknown device {device!r}")
+
+
+def is_torch_tensor(obj) -> bool:
+    mod = type(obj).__module__
+    return mod == "torch" or mod.startswith("torch.")
+
+
+def host_source(arr):
+    """Return (C-contiguous numpy array, B2 dtype code) ready for the b2h_* calls.
+
+    uint16 and float32 go through unchanged (uint16 is shipped over PCIe as uint16); every other
+    dtype gets the reference's ``astype(float32)`` (biahub/deskew.py:578, biahub/register.py:266).
+    """
+    arr = np.asarray(arr)
+    if arr.dtype == np.uint16:
+        code = _cabi.DTYPE_U16
+    else:
+        if arr.dtype != np.float32:
+            with np.errstate(over="ignore"):
+                arr = arr.astype(np.float32)
+        code = _cabi.DTYPE_F32
+    if not arr.flags.c_contiguous:
+        arr = np.ascontiguousarray(arr)
+    if not arr.dtype.isnative:
+        arr = arr.astype(arr.dtype.newbyteorder("="))
+    return arr, code
+
+
+def device_source(tensor):
+    """Return (contiguous CUDA tensor, B2 dtype code) for the b2_* calls."""
+    import torch
+
+    if not tensor.is_cuda:
+        raise RuntimeError(
+            "biahub_b200 computes on the GPU only: pass a CUDA tensor (or a numpy array, which is "
+            "staged through the pinned host pipeline); there is no CPU fallback"
+        )
+    if tensor.dtype == torch.uint16:
+        code = _cabi.DTYPE_U16
+    else:
+        if tensor.dtype != torch.float32:
+            tensor = tensor.to(torch.float32)
+        code = _cabi.DTYPE_F32
+    return tensor.contiguous(), code

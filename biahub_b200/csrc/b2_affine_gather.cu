@@ -1,0 +1,154 @@
+// Generic affine pull warp: one thread per output voxel, float64 coordinates in the oracle's op
+// order, taps fetched with LDG through L1/L2.  Correct for ANY 3x4 matrix, shape and alignment;
+// it is the fallback of the TMA-staged kernels (b2_affine_zsep.cu), not a CPU fallback.
+#include "b2_affine.cuh"
+
+namespace b2 {
+
+template <typename T, int ORDER, int BOUNDARY, bool SCRUB>
+__global__ void __launch_bounds__(256) affine_gather_kernel(const AffineParams p) {
+  const T* __restrict__ src = static_cast<const T*>(p.src);
+  const int64_t total = static_cast<int64_t>(p.oz) * p.oy * p.ox;
+  const int64_t sxy = static_cast<int64_t>(p.sy) * p.sx;
+  for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int x = static_cast<int>(idx % p.ox);
+    const int64_t r = idx / p.ox;
+    const int y = static_cast<int>(r % p.oy);
+    const int z = static_cast<int>(r / p.oy);
+    const double zf = static_cast<double>(z + p.cz);
+    const double yf = static_cast<double>(y + p.cy);
+    const double xf = static_cast<double>(x + p.cx);
+    double c[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const double* m = p.m + 4 * d;
+      c[d] = __dadd_rn(
+          __dadd_rn(__dadd_rn(m[3], __dmul_rn(zf, m[0])), __dmul_rn(yf, m[1])), __dmul_rn(xf, m[2]));
+    }
+    const AxisTap tz = resolve_axis<ORDER, BOUNDARY>(c[0], p.sz);
+    const AxisTap ty = resolve_axis<ORDER, BOUNDARY>(c[1], p.sy);
+    const AxisTap tx = resolve_axis<ORDER, BOUNDARY>(c[2], p.sx);
+    float v = 0.0f;
+    if (tz.inside && ty.inside && tx.inside) {
+      const T* b0 = src + tz.i0 * sxy;
+      if (ORDER == 0) {
+        v = load_tap<T, SCRUB>(b0 + static_cast<int64_t>(ty.i0) * p.sx + tx.i0);
+      } else {
+        const T* b1 = src + tz.i1 * sxy;
+        const int64_t r0 = static_cast<int64_t>(ty.i0) * p.sx;
+        const int64_t r1 = static_cast<int64_t>(ty.i1) * p.sx;
+        const float v000 = load_tap<T, SCRUB>(b0 + r0 + tx.i0);
+        const float v001 = load_tap<T, SCRUB>(b0 + r0 + tx.i1);
+        const float v010 = load_tap<T, SCRUB>(b0 + r1 + tx.i0);
+        const float v011 = load_tap<T, SCRUB>(b0 + r1 + tx.i1);
+        const float v100 = load_tap<T, SCRUB>(b1 + r0 + tx.i0);
+        const float v101 = load_tap<T, SCRUB>(b1 + r0 + tx.i1);
+        const float v110 = load_tap<T, SCRUB>(b1 + r1 + tx.i0);
+        const float v111 = load_tap<T, SCRUB>(b1 + r1 + tx.i1);
+        const float p0 = lerp_w(lerp_w(v000, v001, tx.w), lerp_w(v010, v011, tx.w), ty.w);
+        const float p1 = lerp_w(lerp_w(v100, v101, tx.w), lerp_w(v110, v111, tx.w), ty.w);
+        v = lerp_w(p0, p1, tz.w);
+      }
+    }
+    p.dst[idx] = v;
+  }
+}
+
+template <typename T, int ORDER, int BOUNDARY>
+static int launch_gather_scrub(const AffineParams& p, cudaStream_t stream) {
+  int sms = 148;
+  sm_count(&sms);
+  const int64_t total = static_cast<int64_t>(p.oz) * p.oy * p.ox;
+  if (total == 0) return B2_OK;
+  const int64_t want = (total + 255) / 256;
+  const int64_t cap = static_cast<int64_t>(sms) * 64;
+  const int grid = static_cast<int>(want < cap ? want : cap);
+  if (p.scrub && sizeof(T) == 4)
+    affine_gather_kernel<T, ORDER, BOUNDARY, true><<<grid, 256, 0, stream>>>(p);
+  else
+    affine_gather_kernel<T, ORDER, BOUNDARY, false><<<grid, 256, 0, stream>>>(p);
+  B2_CUDA(cudaGetLastError());
+  count_launch();
+  return B2_OK;
+}
+
+template <typename T>
+static int launch_gather_typed(const AffineParams& p, cudaStream_t stream) {
+  if (p.order == 0) {
+    if (p.boundary == B2_BOUNDARY_CONSTANT)
+      return launch_gather_scrub<T, 0, B2_BOUNDARY_CONSTANT>(p, stream);
+    return launch_gather_scrub<T, 0, B2_BOUNDARY_ITK>(p, stream);
+  }
+  if (p.boundary == B2_BOUNDARY_CONSTANT)
+    return launch_gather_scrub<T, 1, B2_BOUNDARY_CONSTANT>(p, stream);
+  return launch_gather_scrub<T, 1, B2_BOUNDARY_ITK>(p, stream);
+}
+
+int affine_gather_launch(const AffineParams& p, int src_dtype, cudaStream_t stream) {
+  if (src_dtype == B2_DTYPE_U16) return launch_gather_typed<uint16_t>(p, stream);
+  return launch_gather_typed<float>(p, stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+// entry point shared by both affine kernels
+// ---------------------------------------------------------------------------------------------
+int affine_device(const void* src, int src_dtype, int64_t sz, int64_t sy, int64_t sx, float* dst,
+                  int64_t oz, int64_t oy, int64_t ox, const double* M12, const int64_t* crop_start,
+                  int order, int boundary, int scrub, int path, cudaStream_t stream) {
+  if (!src || !dst || !M12) {
+    set_error("affine3d: null pointer");
+    return B2_ERR_INVALID;
+  }
+  if (src_dtype != B2_DTYPE_U16 && src_dtype != B2_DTYPE_F32) {
+    set_error("affine3d: unknown src_dtype %d", src_dtype);
+    return B2_ERR_INVALID;
+  }
+  if (order != 0 && order != 1) {
+    set_error("affine3d: order must be 0 (nearest) or 1 (linear), got %d", order);
+    return B2_ERR_INVALID;
+  }
+  if (boundary != B2_BOUNDARY_CONSTANT && boundary != B2_BOUNDARY_ITK) {
+    set_error("affine3d: unknown boundary %d", boundary);
+    return B2_ERR_INVALID;
+  }
+  const int64_t lim = 2147483647LL;
+  if (sz < 1 || sy < 1 || sx < 1 || oz < 0 || oy < 0 || ox < 0 || sz > lim || sy > lim ||
+      sx > lim || oz > lim || oy > lim || ox > lim) {
+    set_error("affine3d: invalid shape");
+    return B2_ERR_INVALID;
+  }
+  for (int i = 0; i < 12; ++i) {
+    if (!(M12[i] == M12[i]) || M12[i] > 1e300 || M12[i] < -1e300) {
+      set_error("affine3d: matrix entry %d is not finite", i);
+      return B2_ERR_INVALID;
+    }
+  }
+  AffineParams p;
+  p.src = src;
+  p.dst = dst;
+  p.sz = (int)sz; p.sy = (int)sy; p.sx = (int)sx;
+  p.oz = (int)oz; p.oy = (int)oy; p.ox = (int)ox;
+  p.cz = crop_start ? (int)crop_start[0] : 0;
+  p.cy = crop_start ? (int)crop_start[1] : 0;
+  p.cx = crop_start ? (int)crop_start[2] : 0;
+  for (int i = 0; i < 12; ++i) p.m[i] = M12[i];
+  p.order = order;
+  p.boundary = boundary;
+  p.scrub = scrub ? 1 : 0;
+  if (oz == 0 || oy == 0 || ox == 0) return B2_OK;
+
+  if (path != B2_PATH_GATHER) {
+    bool eligible = false;
+    const int rc = affine_zsep_launch(p, src_dtype, stream, &eligible);
+    if (eligible) return rc;
+    if (path == B2_PATH_TMA) {
+      set_error("affine3d: TMA path not eligible (needs a z-separable matrix with m00 > 0, "
+                "16-byte aligned source rows and a plane brick that fits shared memory)");
+      return B2_ERR_UNSUPPORTED;
+    }
+  }
+  return affine_gather_launch(p, src_dtype, stream);
+}
+
+}  // namespace b2

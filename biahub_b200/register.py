@@ -1,0 +1,252 @@
+"""Affine apply path of ``biahub register`` — host-side mirror of reference
+``biahub/register.py:32-281, 397-398``.
+
+``apply_affine_transform`` keeps the reference's signature and matrix convention (4x4
+homogeneous, ZYX, pull: ``source_index = M[:3,:3] @ out_index + M[:3,3]``, no centring —
+reference register.py:148-168, pinned by reference tests/test_affine.py:43-59) and returns a
+float32 array; the resampling runs in libbiahub_b200.so instead of ANTs/ITK or scipy.
+
+``method="ants"`` (default) uses the ITK boundary rule; ``interpolation`` accepts the two ANTs
+modes this path is specified for: ``"linear"`` (order 1) and ``"nearestneighbor"`` (order 0).
+``method="scipy"`` in the reference calls ``scipy.ndimage.affine_transform`` with its default
+cubic spline (order 3) — that is not a linear/nearest resampler and is not built here: it raises
+``NotImplementedError``.  ``affine_warp`` exposes order/boundary explicitly (scipy
+``mode="constant"`` rule = the oracle's primary mode).
+"""
+
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _cabi
+from ._device import device_source, host_source, is_torch_tensor, resolve_device
+
+__all__ = [
+    "get_3D_rescaling_matrix", "get_3D_rotation_matrix", "get_3D_fliplr_matrix",
+    "convert_transform_to_ants", "convert_transform_to_numpy", "apply_affine_transform",
+    "affine_warp", "rescale_voxel_size", "ItkAffineParameters",
+]
+
+_INTERPOLATION_ORDER = {"linear": 1, "nearestneighbor": 0}
+
+
+# ------------------------------------------------------------------------------------------
+# matrix builders (reference register.py:32-145) — YX centre = shape/2
+# ------------------------------------------------------------------------------------------
+def _yx_centres(start_shape_zyx, end_shape_zyx):
+    cy, cx = np.array(start_shape_zyx)[-2:] / 2
+    if end_shape_zyx is None:
+        return cy, cx, cy, cx
+    ey, ex = np.array(end_shape_zyx)[-2:] / 2
+    return cy, cx, ey, ex
+
+
+def get_3D_rescaling_matrix(start_shape_zyx, scaling_factor_zyx=(1, 1, 1), end_shape_zyx=None):
+    cy, cx, ey, ex = _yx_centres(start_shape_zyx, end_shape_zyx)
+    sz, sy, sx = scaling_factor_zyx[-3], scaling_factor_zyx[-2], scaling_factor_zyx[-1]
+    m = np.eye(4)
+    m[0, 0] = sz
+    m[1, 1] = sy
+    m[2, 2] = sx
+    m[1, 3] = -cy * sy + ey
+    m[2, 3] = -cx * sx + ex
+    return m
+
+
+def get_3D_rotation_matrix(start_shape_zyx, angle: float = 0.0, end_shape_zyx=None) -> np.ndarray:
+    cy, cx, ey, ex = _yx_centres(start_shape_zyx, end_shape_zyx)
+    theta = np.radians(angle)
+    c, s = np.cos(theta), np.sin(theta)
+    m = np.eye(4)
+    m[1, 1], m[1, 2] = c, -s
+    m[2, 1], m[2, 2] = s, c
+    m[1, 3] = -cy * c + s * cx + ey
+    m[2, 3] = -cy * s - cx * c + ex
+    return m
+
+
+def get_3D_fliplr_matrix(start_shape_zyx, end_shape_zyx=None) -> np.ndarray:
+    cx_end = (start_shape_zyx[-1] if end_shape_zyx is None else end_shape_zyx[-1]) / 2
+    m = np.eye(4)
+    m[2, 2] = -1
+    m[2, 3] = 2 * cx_end
+    return m
+
+
+def rescale_voxel_size(affine_matrix, input_scale):
+    """Row norms of the linear part times the input scale (reference register.py:397-398)."""
+    return np.linalg.norm(affine_matrix, axis=1) * input_scale
+
+
+# ------------------------------------------------------------------------------------------
+# ITK/ANTs parameter layout (reference register.py:148-199)
+# ------------------------------------------------------------------------------------------
+class ItkAffineParameters:
+    """Stand-in for an ANTs ``AffineTransform``: 12 parameters = row-major 3x3 then translation,
+    plus the fixed parameters (centre).  ``apply_to_image`` resamples with the B200 kernel."""
+
+    transform_type = "AffineTransform"
+    dimension = 3
+
+    def __init__(self, parameters=None, fixed_parameters=None):
+        self.parameters = (np.array([1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0], dtype=np.float64)
+                           if parameters is None else np.asarray(parameters, dtype=np.float64).copy())
+        self.fixed_parameters = (np.zeros(3) if fixed_parameters is None
+                                 else np.asarray(fixed_parameters, dtype=np.float64).copy())
+
+    def set_parameters(self, parameters):
+        parameters = np.asarray(parameters, dtype=np.float64).ravel()
+        if parameters.size != 12:
+            raise ValueError("an affine transform has 12 parameters")
+        self.parameters = parameters.copy()
+
+    def set_fixed_parameters(self, fixed_parameters):
+        self.fixed_parameters = np.asarray(fixed_parameters, dtype=np.float64).ravel().copy()
+
+    def as_matrix(self) -> np.ndarray:
+        return convert_transform_to_numpy(self)
+
+    def apply_to_image(self, image, reference=None, interpolation="linear"):
+        image = np.asarray(image)
+        shape = image.shape if reference is None else np.shape(reference)
+        return affine_warp(image, self.as_matrix(), tuple(shape),
+                           order=_interpolation_order(interpolation), boundary="itk")
+
+
+def convert_transform_to_ants(T_numpy: np.ndarray):
+    """4x4 numpy → ITK-style parameters (reference register.py:148-168)."""
+    T_numpy = np.asarray(T_numpy, dtype=np.float64)
+    assert T_numpy.shape == (4, 4)
+    params = np.concatenate([T_numpy[:3, :3].ravel(), T_numpy[:3, 3]])
+    return ItkAffineParameters(params)
+
+
+def convert_transform_to_numpy(T_ants) -> np.ndarray:
+    """ITK-style parameters → 4x4 numpy, folding the centre into the translation
+    (reference register.py:171-199: t += (I - A) @ centre)."""
+    p = np.asarray(T_ants.parameters, dtype=np.float64)
+    A = p[:9].reshape(3, 3)
+    t = p[9:12] + (np.eye(3) - A) @ np.asarray(T_ants.fixed_parameters, dtype=np.float64)
+    M = np.eye(4)
+    M[:3, :3] = A
+    M[:3, 3] = t
+    return M
+
+
+# ------------------------------------------------------------------------------------------
+# the warp
+# ------------------------------------------------------------------------------------------
+def _interpolation_order(interpolation) -> int:
+    key = str(interpolation).lower()
+    if key not in _INTERPOLATION_ORDER:
+        raise NotImplementedError(
+            f"interpolation={interpolation!r}: the B200 path implements 'linear' and "
+            f"'nearestneighbor' (the modes BASELINE.json's north_star specifies)")
+    return _INTERPOLATION_ORDER[key]
+
+
+def _crop_box(output_shape_zyx, crop_output_slicing):
+    shape = tuple(int(v) for v in output_shape_zyx)
+    if len(shape) != 3:
+        raise ValueError("output_shape_zyx must have 3 entries")
+    if crop_output_slicing is None:
+        return (0, 0, 0), shape
+    starts, sizes = [], []
+    for sl, n in zip(crop_output_slicing, shape):
+        start, stop, step = sl.indices(n)
+        if step != 1:
+            raise ValueError("crop_output_slicing must use unit steps")
+        starts.append(start)
+        sizes.append(max(stop - start, 0))
+    return tuple(starts), tuple(sizes)
+
+
+def affine_warp(data, matrix, output_shape_zyx, order: int = 1, boundary: str = "itk",
+                crop_output_slicing=None, scrub_nonfinite: bool = True, device=None,
+                _path: int = _cabi.PATH_AUTO):
+    """Pull-warp a (Z, Y, X) volume: numpy in → numpy float32 out (host pipeline), or CUDA
+    tensor in → CUDA float32 tensor out (kernel only, on the current stream).
+
+    boundary: ``"itk"`` (ANTs/ITK rule) or ``"constant"`` (scipy ``mode="constant", cval=0``).
+    """
+    bcode = {"itk": _cabi.BOUNDARY_ITK, "constant": _cabi.BOUNDARY_CONSTANT}.get(boundary)
+    if bcode is None:
+        raise ValueError(f"boundary must be 'itk' or 'constant', got {boundary!r}")
+    if order not in (0, 1):
+        raise NotImplementedError("only order 0 (nearest) and 1 (linear) are implemented")
+    starts, sizes = _crop_box(output_shape_zyx, crop_output_slicing)
+    m12 = _cabi.matrix12(matrix)
+    crop = _cabi.int64x3(starts)
+    lib = _cabi.lib()
+
+    if is_torch_tensor(data):
+        import torch
+
+        if data.ndim != 3:
+            raise ValueError("expected a (Z, Y, X) tensor")
+        src, code = device_source(data)
+        with torch.cuda.device(src.device):
+            out = torch.empty(sizes, dtype=torch.float32, device=src.device)
+            if out.numel():
+                _cabi.check(lib.b2_affine3d(
+                    src.data_ptr(), code, *src.shape, out.data_ptr(), *sizes, m12, crop, int(order),
+                    bcode, int(bool(scrub_nonfinite)), int(_path),
+                    torch.cuda.current_stream().cuda_stream))
+        return out
+
+    src, code = host_source(data)
+    if src.ndim != 3:
+        raise ValueError("expected a (Z, Y, X) array")
+    out = np.empty(sizes, dtype=np.float32)
+    if out.size:
+        _cabi.check(lib.b2h_affine3d(
+            src.ctypes.data_as(ctypes.c_void_p), code, *src.shape,
+            out.ctypes.data_as(ctypes.c_void_p), *sizes, m12, crop, int(order), bcode,
+            int(bool(scrub_nonfinite)), resolve_device(device)))
+    return out
+
+
+def apply_affine_transform(
+    zyx_data: np.ndarray,
+    matrix: np.ndarray,
+    output_shape_zyx: tuple,
+    method="ants",
+    interpolation: str = "linear",
+    crop_output_slicing: bool = None,
+) -> np.ndarray:
+    """Drop-in for reference ``apply_affine_transform`` (register.py:202-281).
+
+    3-D (Z, Y, X) or 4-D (C, Z, Y, X) input; NaNs are scrubbed to 0 (and ±inf to ±float32 max,
+    ``np.nan_to_num`` semantics) on load; the result is float32 on ``output_shape_zyx`` cropped
+    to ``crop_output_slicing``.
+    """
+    if method == "ants":
+        order = _interpolation_order(interpolation)
+        boundary = "itk"
+    elif method == "scipy":
+        raise NotImplementedError(
+            "method='scipy' means scipy.ndimage.affine_transform's default cubic spline "
+            "(order=3, reference register.py:272), which the B200 path does not implement; use "
+            "method='ants' or affine_warp(..., boundary='constant', order=0|1)")
+    else:
+        raise ValueError(f"Unknown method {method}")
+
+    ndim = zyx_data.ndim
+    if ndim == 4:
+        _, sizes = _crop_box(output_shape_zyx, crop_output_slicing)
+        if is_torch_tensor(zyx_data):
+            import torch
+
+            return torch.stack([
+                affine_warp(zyx_data[c], matrix, output_shape_zyx, order, boundary,
+                            crop_output_slicing) for c in range(zyx_data.shape[0])])
+        registered = np.zeros((zyx_data.shape[0],) + sizes, dtype=np.float32)
+        for c in range(zyx_data.shape[0]):
+            registered[c] = affine_warp(zyx_data[c], matrix, output_shape_zyx, order, boundary,
+                                        crop_output_slicing)
+        return registered
+    if ndim != 3:
+        raise ValueError("zyx_data must be (Z, Y, X) or (C, Z, Y, X)")
+    return affine_warp(zyx_data, matrix, output_shape_zyx, order, boundary, crop_output_slicing)
