@@ -104,3 +104,23 @@ def device_source(tensor):
             tensor = tensor.to(torch.float32)
         code = _cabi.DTYPE_F32
     return tensor.contiguous(), code
+
+
+def pinned_empty(shape, dtype):
+    """Page-locked host array (numpy view of a pinned torch byte tensor): the b2h_* pipeline
+    copies straight from/to such buffers, skipping its own staging copy."""
+    import torch
+
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    buf = torch.empty(max(n, 1), dtype=torch.uint8, pin_memory=True)
+    return buf.numpy()[:n].view(dtype).reshape(shape)
+
+
+def check_out(out, shape):
+    if out is None:
+        return np.empty(shape, dtype=np.float32)
+    if not (isinstance(out, np.ndarray) and out.dtype == np.float32 and out.shape == tuple(shape)
+            and out.flags.c_contiguous):
+        raise ValueError(f"out must be a C-contiguous float32 array of shape {tuple(shape)}")
+    return out

@@ -29,6 +29,7 @@ struct ZsepGeom {
   int BY, BX;          // brick extent per plane (elements)
   int stage_bytes;     // BY*BX*sizeof(T) rounded up to 128
   int zchunk;          // output planes per CTA
+  int debug;           // fault bisection switches (env B2_ZSEP_DEBUG), 0 in production
 };
 
 template <typename T>
@@ -83,8 +84,12 @@ __global__ void __launch_bounds__(kZsThreads)
   }
   // clamp far-away tiles so the int conversion is defined; such tiles are entirely outside
   const double big = 1.0e9;
+  // The innermost TMA coordinate must be 16-byte aligned (measured on B200 / driver 580: an
+  // unaligned inner coordinate raises "illegal instruction"), so the brick starts at the
+  // 16-byte boundary at or below the back-projected minimum.
+  constexpr int kVec = 16 / static_cast<int>(sizeof(T));
   const int by0 = __double2int_rd(fmax(-big, fmin(big, cy_min)));
-  const int bx0 = __double2int_rd(fmax(-big, fmin(big, cx_min)));
+  const int bx0 = __double2int_rd(fmax(-big, fmin(big, cx_min))) & ~(kVec - 1);
   const int by_hi = __double2int_rd(fmax(-big, fmin(big, cy_max))) + 1;
   const int bx_hi = __double2int_rd(fmax(-big, fmin(big, cx_max))) + 1;
   const bool brick_ok = (by_hi - by0) < g.BY && (bx_hi - bx0) < g.BX;  // CTA-uniform
@@ -102,8 +107,9 @@ __global__ void __launch_bounds__(kZsThreads)
   const double m00 = p.m[0], t0 = p.m[3];
 
   if (tid >= kZsConsumers) {
-    // =========================== producer warp (one elected lane) ===========================
-    if (tid == kZsConsumers && brick_ok) {
+    // ================= producer warp: all lanes walk the plane sequence, lane 0 issues =================
+    if (brick_ok) {
+      const bool issuer = (tid == kZsConsumers);
       int s_last = INT_MIN;
       uint32_t seq = 0;
       for (int z = zb; z < ze; ++z) {
@@ -115,9 +121,19 @@ __global__ void __launch_bounds__(kZsThreads)
           const int s = h ? tz.i1 : tz.i0;
           if (s > s_last) {
             const uint32_t stage = seq % kZsStages;
-            if (seq >= kZsStages) mbar_wait(&empty_bar[stage], ((seq / kZsStages) - 1) & 1);
-            mbar_expect_tx(&full_bar[stage], static_cast<uint32_t>(g.BY) * g.BX * sizeof(T));
-            tma_load_3d(stage0 + stage * g.stage_bytes, &src_map, &full_bar[stage], bx0, by0, s);
+            if (!(g.debug & 1)) {
+              if (seq >= kZsStages && !(g.debug & 2))
+                mbar_wait(&empty_bar[stage], ((seq / kZsStages) - 1) & 1);
+              if (issuer) {
+                if (g.debug & 4) {
+                  mbar_arrive(&full_bar[stage]);
+                } else {
+                  mbar_expect_tx(&full_bar[stage], static_cast<uint32_t>(g.BY) * g.BX * sizeof(T));
+                  tma_load_3d(stage0 + stage * g.stage_bytes, &src_map, &full_bar[stage], bx0, by0, s);
+                }
+              }
+              __syncwarp();
+            }
             s_last = s;
             ++seq;
           }
@@ -189,7 +205,7 @@ __global__ void __launch_bounds__(kZsThreads)
         const T* gplane = nullptr;
         const uint32_t stage = seq % kZsStages;
         if (brick_ok) {
-          mbar_wait(&full_bar[stage], (seq / kZsStages) & 1);
+          if (!(g.debug & 1)) mbar_wait(&full_bar[stage], (seq / kZsStages) & 1);
           base = stage0 + stage * g.stage_bytes;
         } else {
           gplane = src + s * sxy;
@@ -228,7 +244,7 @@ __global__ void __launch_bounds__(kZsThreads)
           }
           p_last[i] = v;
         }
-        if (brick_ok) {
+        if (brick_ok && !(g.debug & 3)) {
           __syncwarp();
           if ((tid & 31) == 0) mbar_arrive(&empty_bar[stage]);
         }
@@ -264,7 +280,7 @@ static bool zsep_geometry(const AffineParams& p, ZsepGeom* g, size_t* smem_bytes
   if (!(ey < 250.0) || !(ex < 250.0)) return false;
   const int vec = 16 / sizeof(T);
   int BY = static_cast<int>(ey) + 4;
-  int BX = static_cast<int>(ex) + 4;
+  int BX = static_cast<int>(ex) + 4 + (vec - 1);  // + alignment slack of the brick origin
   BX = (BX + vec - 1) / vec * vec;
   if (BY > 256 || BX > 256) return false;
   const int stage = (BY * BX * static_cast<int>(sizeof(T)) + 127) / 128 * 128;
@@ -313,6 +329,10 @@ static int launch_zsep(const AffineParams& p, ZsepGeom g, size_t smem_bytes, cud
   if (zchunk < 8) zchunk = 8;
   if (zchunk > p.oz) zchunk = p.oz;
   g.zchunk = zchunk;
+  {
+    const char* dbg = getenv("B2_ZSEP_DEBUG");
+    g.debug = dbg ? atoi(dbg) : 0;
+  }
   const int grid_z = (p.oz + zchunk - 1) / zchunk;
   if (tiles_y > 65535 || grid_z > 65535) return affine_gather_launch(p, sizeof(T) == 2 ? 0 : 1, stream);
 

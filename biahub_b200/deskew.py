@@ -20,7 +20,7 @@ from typing import Literal
 import numpy as np
 
 from . import _cabi
-from ._device import device_source, host_source, is_torch_tensor, resolve_device
+from ._device import check_out, device_source, host_source, is_torch_tensor, resolve_device
 
 __all__ = [
     "_average_n_slices", "_get_averaged_shape", "_get_transform_matrix", "get_deskewed_data_shape",
@@ -171,7 +171,7 @@ def fast_deskew_zyx(
 
 
 def _deskew_host(zyx, device, ls_angle_deg, px_to_scan_ratio, keep_overhang, average_n_slices=1,
-                 overhang_fill=0):
+                 overhang_fill=0, out=None):
     """numpy (Z, Y, X) → numpy float32 through the pinned-buffer host pipeline."""
     do_fill, _, _ = _fill_args(keep_overhang, overhang_fill)
     dev = resolve_device(device)
@@ -184,14 +184,18 @@ def _deskew_host(zyx, device, ls_angle_deg, px_to_scan_ratio, keep_overhang, ave
             t = torch.from_numpy(src.view(np.int16)).to(f"cuda:{dev}").view(torch.uint16)
         else:
             t = torch.from_numpy(src).to(f"cuda:{dev}")
-        out = fast_deskew_zyx(t, ls_angle_deg, px_to_scan_ratio, keep_overhang, average_n_slices,
+        res = fast_deskew_zyx(t, ls_angle_deg, px_to_scan_ratio, keep_overhang, average_n_slices,
                               overhang_fill)
-        return out.cpu().numpy()
+        if out is None:
+            return res.cpu().numpy()
+        out = check_out(out, tuple(res.shape))
+        torch.from_numpy(out).copy_(res)
+        return out
     src, code = host_source(zyx)
     if src.ndim != 3:
         raise ValueError("raw data must have ndim == 3 (Z, Y, X)")
     s = deskew_scalars(src.shape, ls_angle_deg, px_to_scan_ratio, keep_overhang, average_n_slices)
-    out = np.empty((s["Zavg"], s["Yo"], s["Xo"]), dtype=np.float32)
+    out = check_out(out, (s["Zavg"], s["Yo"], s["Xo"]))
     _cabi.check(_cabi.lib().b2h_deskew(
         src.ctypes.data_as(ctypes.c_void_p), code, s["Zi"], s["Yi"], s["Xi"],
         out.ctypes.data_as(ctypes.c_void_p), s["Zavg"], s["Yo"], s["Xo"], s["Zo"], s["N"],
@@ -229,12 +233,13 @@ def _deskew_czyx(data, **kwargs):
     return deskew_zyx(data[0], **kwargs)[None]
 
 
-def _fast_deskew_czyx(data, device="cuda", num_splits=1, **kwargs):
+def _fast_deskew_czyx(data, device="cuda", num_splits=1, out=None, **kwargs):
     """CZYX wrapper used by ``biahub deskew`` (reference deskew.py:551-579): takes ``data[0]``,
     returns ``(1, Z', Y', X')`` float32.  ``num_splits`` is accepted for compatibility: the
     kernel is tile-based and the host pipeline already streams the volume in slabs, so no
-    host-side split/concatenate is needed (splitting along input X is exact)."""
+    host-side split/concatenate is needed (splitting along input X is exact).
+    ``out`` (extension): optional float32 (Z', Y', X') destination, e.g. a pinned buffer."""
     zyx = np.asarray(data)[0]
     if int(num_splits) < 1:
         raise ValueError("num_splits must be >= 1")
-    return _deskew_host(zyx, device, **kwargs)[None]
+    return _deskew_host(zyx, device, out=out, **kwargs)[None]

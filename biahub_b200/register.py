@@ -21,7 +21,7 @@ import ctypes
 import numpy as np
 
 from . import _cabi
-from ._device import device_source, host_source, is_torch_tensor, resolve_device
+from ._device import check_out, device_source, host_source, is_torch_tensor, resolve_device
 
 __all__ = [
     "get_3D_rescaling_matrix", "get_3D_rotation_matrix", "get_3D_fliplr_matrix",
@@ -165,7 +165,7 @@ def _crop_box(output_shape_zyx, crop_output_slicing):
 
 def affine_warp(data, matrix, output_shape_zyx, order: int = 1, boundary: str = "itk",
                 crop_output_slicing=None, scrub_nonfinite: bool = True, device=None,
-                _path: int = _cabi.PATH_AUTO):
+                out=None, _path: int = _cabi.PATH_AUTO):
     """Pull-warp a (Z, Y, X) volume: numpy in → numpy float32 out (host pipeline), or CUDA
     tensor in → CUDA float32 tensor out (kernel only, on the current stream).
 
@@ -199,7 +199,7 @@ def affine_warp(data, matrix, output_shape_zyx, order: int = 1, boundary: str = 
     src, code = host_source(data)
     if src.ndim != 3:
         raise ValueError("expected a (Z, Y, X) array")
-    out = np.empty(sizes, dtype=np.float32)
+    out = check_out(out, sizes)
     if out.size:
         _cabi.check(lib.b2h_affine3d(
             src.ctypes.data_as(ctypes.c_void_p), code, *src.shape,

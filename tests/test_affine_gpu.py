@@ -1,0 +1,214 @@
+"""GPU parity tests for the affine apply path of register / stabilize (through the C ABI)."""
+import numpy as np
+import pytest
+
+from oracle import affine_oracle as ao
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4  # of the input dynamic range, order 1 (north_star); order 0 / integer shifts: bit-exact
+
+
+def _vol(shape, seed, nan_frac=0.0):
+    rng = np.random.default_rng(seed)
+    v = (rng.random(shape, dtype=np.float32) * np.float32(4095.0)).astype(np.float32)
+    if nan_frac:
+        m = rng.random(shape) < nan_frac
+        v[m] = np.nan
+        v.flat[7] = np.inf
+        v.flat[11] = -np.inf
+    return v
+
+
+def _to_cuda(arr):
+    import torch
+
+    if arr.dtype == np.uint16:
+        return torch.from_numpy(arr.view(np.int16)).cuda().view(torch.uint16)
+    return torch.from_numpy(arr).cuda()
+
+
+def _compare(got, want, order, rng=4095.0, name=""):
+    assert got.shape == want.shape and got.dtype == np.float32, name
+    if order == 0:
+        assert np.array_equal(got, want), f"{name}: {np.sum(got != want)} voxels differ"
+    else:
+        big = np.abs(want) > 1e30  # taps scrubbed from +-inf: compare relatively
+        err = np.abs(got[~big].astype(np.float64) - want[~big]).max()
+        assert err <= TOL * rng, f"{name}: max err {err}"
+        if big.any():
+            assert np.allclose(got[big], want[big], rtol=1e-5)
+
+
+def test_golden_scipy_vectors(golden):
+    from biahub_b200 import affine_warp
+
+    arrays, meta = golden
+    vol = arrays["affine_in"]
+    for c in meta["affine"]:
+        want = arrays[f"affine_{c['name']}_o{c['order']}"]
+        got = affine_warp(vol, np.array(c["matrix"]), tuple(c["out_shape"]), order=c["order"],
+                          boundary="constant")
+        _compare(got, want, c["order"], name=f"{c['name']}/o{c['order']}")
+
+
+MATRICES = {
+    "c3": lambda s: ao.register_matrix_c3(s),
+    "int_shift": lambda s: ao.translation_matrix_zyx((-3, 1, 4)),
+    "frac_shift": lambda s: ao.translation_matrix_zyx((0.4, -2.25, 3.5)),
+    "zscale": lambda s: ao.translation_matrix_zyx((0.3, 1.5, -2.0)) @ ao.scaling_matrix_zyx(s, (0.5, 1.0, 1.0)),
+    "zscale_up": lambda s: ao.scaling_matrix_zyx(s, (2.5, 0.9, 1.1)),
+    "fliplr": lambda s: np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, -1, s[2] - 1.0], [0, 0, 0, 1.0]]),
+    "generic": lambda s: np.array([[0.98, 0.05, -0.03, 1.2], [0.04, 1.02, 0.11, -3.3],
+                                   [-0.06, -0.09, 0.95, 4.7], [0, 0, 0, 1.0]]),
+    "zflip": lambda s: np.array([[-1, 0, 0, s[0] - 1.0], [0, 1, 0, 0.5], [0, 0, 1, 0], [0, 0, 0, 1.0]]),
+}
+
+
+@pytest.mark.parametrize("path", ["auto", "gather"])
+@pytest.mark.parametrize("boundary", ["constant", "itk"])
+@pytest.mark.parametrize("order", [0, 1])
+@pytest.mark.parametrize("mname", sorted(MATRICES))
+def test_device_api_matches_oracle(mname, order, boundary, path):
+    import torch
+
+    from biahub_b200 import _cabi, affine_warp
+
+    shape = (20, 72, 136)
+    vol = _vol(shape, seed=3, nan_frac=0.001)
+    M = MATRICES[mname](shape)
+    out_shape = (22, 70, 140)
+    want = ao.affine_oracle_numpy(vol, M, out_shape, order, boundary)
+    p = _cabi.PATH_GATHER if path == "gather" else _cabi.PATH_AUTO
+    got = affine_warp(_to_cuda(vol), M, out_shape, order=order, boundary=boundary, _path=p)
+    torch.cuda.synchronize()
+    _compare(got.cpu().numpy(), want, order, name=f"{mname}/{order}/{boundary}/{path}")
+
+
+@pytest.mark.parametrize("mname", ["c3", "frac_shift", "int_shift", "zscale"])
+def test_tma_path_is_taken_and_matches_gather(mname):
+    """The z-separable matrices must be eligible for the TMA brick kernel (PATH_TMA raises
+    otherwise) and agree with the independent gather kernel."""
+    import torch
+
+    from biahub_b200 import _cabi, affine_warp
+
+    shape = (24, 200, 264)
+    vol = _vol(shape, seed=9)
+    M = MATRICES[mname](shape)
+    t = _to_cuda(vol)
+    for order in (0, 1):
+        for boundary in ("constant", "itk"):
+            a = affine_warp(t, M, shape, order=order, boundary=boundary, _path=_cabi.PATH_TMA)
+            b = affine_warp(t, M, shape, order=order, boundary=boundary, _path=_cabi.PATH_GATHER)
+            if order == 0:
+                assert torch.equal(a, b)
+            else:
+                assert (a - b).abs().max().item() <= 1e-6 * 4095.0
+
+
+def test_generic_matrix_not_tma_eligible():
+    from biahub_b200 import _cabi, affine_warp
+    from biahub_b200._cabi import B2Unsupported
+
+    vol = _vol((8, 64, 64), seed=1)
+    with pytest.raises(B2Unsupported):
+        affine_warp(_to_cuda(vol), MATRICES["generic"](vol.shape), vol.shape, _path=_cabi.PATH_TMA)
+
+
+def test_uint16_source_and_crop():
+    from biahub_b200 import affine_warp
+
+    rng = np.random.default_rng(5)
+    vol = rng.integers(0, 65536, size=(18, 80, 128), dtype=np.uint16)
+    M = ao.register_matrix_c3(vol.shape)
+    crop = (slice(2, 15), slice(5, 70), slice(16, 120))
+    for order in (0, 1):
+        want = ao.affine_oracle_numpy(vol, M, vol.shape, order, "itk", crop_output_slicing=crop)
+        got = affine_warp(vol, M, vol.shape, order=order, boundary="itk", crop_output_slicing=crop)
+        _compare(got, want, order, rng=65535.0, name=f"u16/crop/o{order}")
+        got_d = affine_warp(_to_cuda(vol), M, vol.shape, order=order, boundary="itk",
+                            crop_output_slicing=crop).cpu().numpy()
+        assert np.array_equal(got, got_d)
+
+
+def test_reference_known_answers():
+    """reference tests/test_affine.py:26-59."""
+    from biahub_b200 import apply_affine_transform
+
+    ones = np.ones((10, 10, 10))
+    for interp in ("linear", "nearestneighbor"):
+        out = apply_affine_transform(ones, np.eye(4), (10, 10, 10), interpolation=interp)
+        assert isinstance(out, np.ndarray) and out.shape == (10, 10, 10)
+        assert np.all(out == 1)
+    M = np.eye(4)
+    M[:3, -1] = (-3, 1, 4)
+    out = apply_affine_transform(ones, M, (10, 10, 10))
+    assert out.shape == (10, 10, 10) and out.dtype == np.float32
+    assert np.all(out[3:10, 0:9, 0:6] == 1)
+    assert out.sum() == 7 * 9 * 6
+    with pytest.raises(ValueError, match="Unknown method"):
+        apply_affine_transform(ones, M, (10, 10, 10), method="cupy")
+    # 4-D input → per-channel loop (reference register.py:240-251)
+    out4 = apply_affine_transform(np.ones((2, 10, 10, 10)), M, (10, 10, 10),
+                                  crop_output_slicing=(slice(3, 10), slice(0, 9), slice(0, 6)))
+    assert out4.shape == (2, 7, 9, 6) and np.all(out4 == 1)
+
+
+def test_stabilize_integer_translations_bit_exact():
+    """Z-focus stabilisation matrices carry integer shifts: output must be a bit-exact shifted copy
+    (zero outside), for every timepoint of a random-walk list."""
+    from biahub_b200 import apply_stabilization_transform
+
+    rng = np.random.default_rng(8)
+    czyx = _vol((2, 12, 96, 160), seed=4)
+    shifts = np.cumsum(rng.integers(-3, 4, size=(5, 3)), axis=0)
+    mats = []
+    for s in shifts:
+        m = np.eye(4)
+        m[:3, 3] = s
+        mats.append(m)
+    for t in range(len(mats)):
+        out = apply_stabilization_transform(czyx, mats, t)
+        assert out.shape == czyx.shape and out.dtype == np.float32
+        dz, dy, dx = (int(v) for v in shifts[t])
+        want = np.zeros_like(czyx)
+        Z, Y, X = czyx.shape[1:]
+        zs = slice(max(0, -dz), min(Z, Z - dz)); ys = slice(max(0, -dy), min(Y, Y - dy)); xs = slice(max(0, -dx), min(X, X - dx))
+        zi = slice(zs.start + dz, zs.stop + dz); yi = slice(ys.start + dy, ys.stop + dy); xi = slice(xs.start + dx, xs.stop + dx)
+        want[:, zs, ys, xs] = czyx[:, zi, yi, xi]
+        assert np.array_equal(out, want), t
+
+
+def test_stabilize_fractional_and_output_shape():
+    from biahub_b200 import apply_stabilization_transform
+
+    zyx = _vol((10, 64, 96), seed=6, nan_frac=0.002)
+    mats = [np.eye(4) for _ in range(3)]
+    mats[2][:3, 3] = (0.75, -1.5, 2.25)
+    out = apply_stabilization_transform(zyx, mats, 2, output_shape=(12, 60, 100))
+    want = ao.affine_oracle_numpy(zyx, mats[2], (12, 60, 100), 1, "itk")
+    _compare(out, want, 1, name="stabilize/frac")
+
+
+def test_full_size_spot_check_c3_plane_count():
+    """C3-like geometry at full YX size (few planes): TMA kernel vs the float64 oracle on a random
+    sample of voxels plus the volume corners."""
+    import torch
+
+    from biahub_b200 import _cabi, affine_warp
+
+    shape = (6, 2048, 2048)
+    vol = _vol(shape, seed=2000)
+    M = ao.register_matrix_c3(shape)
+    got = affine_warp(_to_cuda(vol), M, shape, order=1, boundary="constant", _path=_cabi.PATH_TMA)
+    torch.cuda.synchronize()
+    got = got.cpu().numpy()
+    rng = np.random.default_rng(1)
+    pts = np.stack([rng.integers(0, s, size=50000) for s in shape], axis=1)
+    want = ao.affine_oracle_points(vol, M, pts, 1, "constant")
+    err = np.abs(got[pts[:, 0], pts[:, 1], pts[:, 2]].astype(np.float64) - want).max()
+    assert err <= TOL * 4095.0
+    got0 = affine_warp(_to_cuda(vol), M, shape, order=0, boundary="constant").cpu().numpy()
+    want0 = ao.affine_oracle_points(vol, M, pts, 0, "constant")
+    assert np.array_equal(got0[pts[:, 0], pts[:, 1], pts[:, 2]], want0)
