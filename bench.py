@@ -141,6 +141,16 @@ def stabilize_matrices(n, seed=3000):
     return mats
 
 
+def register_matrix_c3(shape, angle_deg=7.3, scale_yx=1.07, shift_zyx=(0.4, 3.25, -11.5)):
+    """C3 matrix from the package's own builders (reference register.py:32-111)."""
+    import biahub_b200 as b2
+
+    T = np.eye(4)
+    T[:3, 3] = shift_zyx
+    return (T @ b2.get_3D_rotation_matrix(shape, angle_deg)
+            @ b2.get_3D_rescaling_matrix(shape, (1.0, scale_yx, scale_yx)))
+
+
 def unit_geometry(w):
     """(out_shape, algorithmic bytes per unit, output voxels per unit)."""
     import biahub_b200 as b2
@@ -165,7 +175,6 @@ def run_b200(args, w, rank, world, local_rank):
     import biahub_b200 as b2
     from biahub_b200 import _cabi
     from biahub_b200._device import pinned_empty
-    from oracle import affine_oracle as ao  # matrix builder for the C3 workload only
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -193,7 +202,7 @@ def run_b200(args, w, rank, world, local_rank):
         else:
             srcs.append(torch.rand((Z, Y, X), generator=gen, device=dev, dtype=torch.float32) * 4095.0)
     if w["kind"] == "register":
-        mats = [ao.register_matrix_c3(w["shape"])] * units
+        mats = [register_matrix_c3(w["shape"])] * units
     elif w["kind"] == "stabilize":
         mats = stabilize_matrices(units)
     outs = [None] * units
