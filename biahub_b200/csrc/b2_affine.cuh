@@ -83,6 +83,43 @@ __device__ __forceinline__ float lerp_w(float v0, float v1, float w) {
   return __fmaf_rn(w, v1, __fmul_rn(__fsub_rn(1.0f, w), v0));
 }
 
+// One output voxel of the generic warp: float64 coordinates in the oracle's op order, taps via LDG.
+template <typename T, int ORDER, int BOUNDARY, bool SCRUB>
+__device__ __forceinline__ float affine_sample_generic(const AffineParams& p, int z, int y, int x) {
+  const T* __restrict__ src = static_cast<const T*>(p.src);
+  const int64_t sxy = static_cast<int64_t>(p.sy) * p.sx;
+  const double zf = static_cast<double>(z + p.cz);
+  const double yf = static_cast<double>(y + p.cy);
+  const double xf = static_cast<double>(x + p.cx);
+  double c[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const double* m = p.m + 4 * d;
+    c[d] = __dadd_rn(
+        __dadd_rn(__dadd_rn(m[3], __dmul_rn(zf, m[0])), __dmul_rn(yf, m[1])), __dmul_rn(xf, m[2]));
+  }
+  const AxisTap tz = resolve_axis<ORDER, BOUNDARY>(c[0], p.sz);
+  const AxisTap ty = resolve_axis<ORDER, BOUNDARY>(c[1], p.sy);
+  const AxisTap tx = resolve_axis<ORDER, BOUNDARY>(c[2], p.sx);
+  if (!(tz.inside && ty.inside && tx.inside)) return 0.0f;
+  const T* b0 = src + tz.i0 * sxy;
+  if (ORDER == 0) return load_tap<T, SCRUB>(b0 + static_cast<int64_t>(ty.i0) * p.sx + tx.i0);
+  const T* b1 = src + tz.i1 * sxy;
+  const int64_t r0 = static_cast<int64_t>(ty.i0) * p.sx;
+  const int64_t r1 = static_cast<int64_t>(ty.i1) * p.sx;
+  const float v000 = load_tap<T, SCRUB>(b0 + r0 + tx.i0);
+  const float v001 = load_tap<T, SCRUB>(b0 + r0 + tx.i1);
+  const float v010 = load_tap<T, SCRUB>(b0 + r1 + tx.i0);
+  const float v011 = load_tap<T, SCRUB>(b0 + r1 + tx.i1);
+  const float v100 = load_tap<T, SCRUB>(b1 + r0 + tx.i0);
+  const float v101 = load_tap<T, SCRUB>(b1 + r0 + tx.i1);
+  const float v110 = load_tap<T, SCRUB>(b1 + r1 + tx.i0);
+  const float v111 = load_tap<T, SCRUB>(b1 + r1 + tx.i1);
+  const float p0 = lerp_w(lerp_w(v000, v001, tx.w), lerp_w(v010, v011, tx.w), ty.w);
+  const float p1 = lerp_w(lerp_w(v100, v101, tx.w), lerp_w(v110, v111, tx.w), ty.w);
+  return lerp_w(p0, p1, tz.w);
+}
+
 #endif  // __CUDACC__
 
 int affine_gather_launch(const AffineParams& p, int src_dtype, cudaStream_t stream);

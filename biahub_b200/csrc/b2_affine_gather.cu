@@ -7,50 +7,14 @@ namespace b2 {
 
 template <typename T, int ORDER, int BOUNDARY, bool SCRUB>
 __global__ void __launch_bounds__(256) affine_gather_kernel(const AffineParams p) {
-  const T* __restrict__ src = static_cast<const T*>(p.src);
   const int64_t total = static_cast<int64_t>(p.oz) * p.oy * p.ox;
-  const int64_t sxy = static_cast<int64_t>(p.sy) * p.sx;
   for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
        idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int x = static_cast<int>(idx % p.ox);
     const int64_t r = idx / p.ox;
     const int y = static_cast<int>(r % p.oy);
     const int z = static_cast<int>(r / p.oy);
-    const double zf = static_cast<double>(z + p.cz);
-    const double yf = static_cast<double>(y + p.cy);
-    const double xf = static_cast<double>(x + p.cx);
-    double c[3];
-#pragma unroll
-    for (int d = 0; d < 3; ++d) {
-      const double* m = p.m + 4 * d;
-      c[d] = __dadd_rn(
-          __dadd_rn(__dadd_rn(m[3], __dmul_rn(zf, m[0])), __dmul_rn(yf, m[1])), __dmul_rn(xf, m[2]));
-    }
-    const AxisTap tz = resolve_axis<ORDER, BOUNDARY>(c[0], p.sz);
-    const AxisTap ty = resolve_axis<ORDER, BOUNDARY>(c[1], p.sy);
-    const AxisTap tx = resolve_axis<ORDER, BOUNDARY>(c[2], p.sx);
-    float v = 0.0f;
-    if (tz.inside && ty.inside && tx.inside) {
-      const T* b0 = src + tz.i0 * sxy;
-      if (ORDER == 0) {
-        v = load_tap<T, SCRUB>(b0 + static_cast<int64_t>(ty.i0) * p.sx + tx.i0);
-      } else {
-        const T* b1 = src + tz.i1 * sxy;
-        const int64_t r0 = static_cast<int64_t>(ty.i0) * p.sx;
-        const int64_t r1 = static_cast<int64_t>(ty.i1) * p.sx;
-        const float v000 = load_tap<T, SCRUB>(b0 + r0 + tx.i0);
-        const float v001 = load_tap<T, SCRUB>(b0 + r0 + tx.i1);
-        const float v010 = load_tap<T, SCRUB>(b0 + r1 + tx.i0);
-        const float v011 = load_tap<T, SCRUB>(b0 + r1 + tx.i1);
-        const float v100 = load_tap<T, SCRUB>(b1 + r0 + tx.i0);
-        const float v101 = load_tap<T, SCRUB>(b1 + r0 + tx.i1);
-        const float v110 = load_tap<T, SCRUB>(b1 + r1 + tx.i0);
-        const float v111 = load_tap<T, SCRUB>(b1 + r1 + tx.i1);
-        const float p0 = lerp_w(lerp_w(v000, v001, tx.w), lerp_w(v010, v011, tx.w), ty.w);
-        const float p1 = lerp_w(lerp_w(v100, v101, tx.w), lerp_w(v110, v111, tx.w), ty.w);
-        v = lerp_w(p0, p1, tz.w);
-      }
-    }
+    const float v = affine_sample_generic<T, ORDER, BOUNDARY, SCRUB>(p, z, y, x);
     p.dst[idx] = v;
   }
 }

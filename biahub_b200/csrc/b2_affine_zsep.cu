@@ -8,11 +8,12 @@
 // in-plane source footprint is the same for every z: the back-projected bounding box of the
 // tile, a (BY x BX) brick per source plane.  A producer warp streams the needed source planes
 // through a ring of shared-memory stages with 3-D TMA box loads (out-of-bounds zero fill);
-// consumer threads hold their in-plane tap offsets/weights in registers (computed once, in
-// float64, in the oracle's op order), reduce each arriving plane to one in-plane-interpolated
-// value per output point, and blend consecutive planes along z.  Every source plane brick is
-// read from global memory exactly once per CTA and every output voxel is written once,
-// coalesced along x.
+// consumer threads hold, per output point, ONE brick offset and FOUR bilinear weights in
+// registers (computed once, in float64, in the oracle's op order), reduce each arriving plane
+// to one in-plane-interpolated value per point (4 LDS + 4 FMA), and blend consecutive planes
+// along z (2 FMA).  The per-z tap table (plane indices + weights) is computed once per CTA into
+// shared memory.  Every source plane brick is read from global memory exactly once per CTA and
+// every output voxel is written once, coalesced along x.
 #include "b2_affine.cuh"
 
 namespace b2 {
@@ -24,26 +25,26 @@ constexpr int kZsThreads = kZsConsumers + 32;  // + one producer warp
 constexpr int kZsStages = 4;
 constexpr int kZsPPT = (kZsTY * kZsTX) / kZsConsumers;  // output points per consumer thread
 constexpr int kZsRowsPerPass = kZsConsumers / kZsTX;
+constexpr int kZsMaxChunk = 128;  // output planes per CTA (size of the z tap table)
 
 struct ZsepGeom {
-  int BY, BX;          // brick extent per plane (elements)
-  int stage_bytes;     // BY*BX*sizeof(T) rounded up to 128
-  int zchunk;          // output planes per CTA
-  int debug;           // fault bisection switches (env B2_ZSEP_DEBUG), 0 in production
+  int BY, BX;       // brick extent per plane (elements)
+  int stage_bytes;  // BY*BX*sizeof(T) rounded up to 128
+  int zchunk;       // output planes per CTA (<= kZsMaxChunk)
 };
 
 template <typename T>
-__device__ __forceinline__ float lds_elem(uint32_t base, int off);
+__device__ __forceinline__ float lds_elem(uint32_t addr);
 template <>
-__device__ __forceinline__ float lds_elem<float>(uint32_t base, int off) {
+__device__ __forceinline__ float lds_elem<float>(uint32_t addr) {
   float v;
-  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(base + static_cast<uint32_t>(off) * 4u));
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
   return v;
 }
 template <>
-__device__ __forceinline__ float lds_elem<uint16_t>(uint32_t base, int off) {
+__device__ __forceinline__ float lds_elem<uint16_t>(uint32_t addr) {
   unsigned short v;
-  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(base + static_cast<uint32_t>(off) * 2u));
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
   return static_cast<float>(v);
 }
 
@@ -52,20 +53,40 @@ __device__ __forceinline__ double coord_yx(double yf, double xf, const double* m
   return __dadd_rn(__dadd_rn(m[3], __dmul_rn(yf, m[1])), __dmul_rn(xf, m[2]));
 }
 
+// Rare path: the host-side bound on the brick size was too tight for this tile (never expected):
+// every thread of the CTA resamples the tile straight from global memory.
 template <typename T, int ORDER, int BOUNDARY, bool SCRUB>
-__global__ void __launch_bounds__(kZsThreads)
+__device__ __noinline__ void zsep_tile_from_global(const AffineParams& p, int y0, int x0, int zb,
+                                                   int ze) {
+  const int n = (ze - zb) * kZsTY * kZsTX;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int x = x0 + i % kZsTX;
+    const int y = y0 + (i / kZsTX) % kZsTY;
+    const int z = zb + i / (kZsTX * kZsTY);
+    if (y < p.oy && x < p.ox)
+      p.dst[(static_cast<int64_t>(z) * p.oy + y) * p.ox + x] =
+          affine_sample_generic<T, ORDER, BOUNDARY, SCRUB>(p, z, y, x);
+  }
+}
+
+template <typename T, int ORDER, int BOUNDARY, bool SCRUB>
+__global__ void __launch_bounds__(kZsThreads, 3)
     affine_zsep_kernel(const __grid_constant__ CUtensorMap src_map, const AffineParams p,
                        const ZsepGeom g) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[kZsStages];
   __shared__ uint64_t empty_bar[kZsStages];
+  // per output plane of this CTA: {i0 (or -1 when outside), i1, bits(w0), bits(w1)}
+  __shared__ int4 ztab[kZsMaxChunk];
 
+  constexpr int kVec = 16 / static_cast<int>(sizeof(T));
   const uint32_t stage0 = (smem_u32(smem_raw) + 127u) & ~127u;
   const int tid = threadIdx.x;
   const int y0 = blockIdx.y * kZsTY;
   const int x0 = blockIdx.x * kZsTX;
   const int zb = blockIdx.z * g.zchunk;
   const int ze = min(zb + g.zchunk, p.oz);
+  const int nz = ze - zb;
 
   // ---- brick origin: back-project the tile's four corners (uniform across the CTA)
   const int yl = min(y0 + kZsTY - 1, p.oy - 1);
@@ -82,17 +103,21 @@ __global__ void __launch_bounds__(kZsThreads)
     cx_min = fmin(cx_min, cx);
     cx_max = fmax(cx_max, cx);
   }
-  // clamp far-away tiles so the int conversion is defined; such tiles are entirely outside
-  const double big = 1.0e9;
+  // Clamp far-away tiles so the int conversion is defined (such tiles are entirely outside).
   // The innermost TMA coordinate must be 16-byte aligned (measured on B200 / driver 580: an
-  // unaligned inner coordinate raises "illegal instruction"), so the brick starts at the
-  // 16-byte boundary at or below the back-projected minimum.
-  constexpr int kVec = 16 / static_cast<int>(sizeof(T));
+  // unaligned inner coordinate raises "illegal instruction"), so the brick starts at the 16-byte
+  // boundary at or below the back-projected minimum.  Taps are always (i0, i0+1) with the clamped
+  // neighbour's weight forced to 0, so the brick must reach floor(max)+2 when i0 was clamped up.
+  const double big = 1.0e9;
   const int by0 = __double2int_rd(fmax(-big, fmin(big, cy_min)));
   const int bx0 = __double2int_rd(fmax(-big, fmin(big, cx_min))) & ~(kVec - 1);
-  const int by_hi = __double2int_rd(fmax(-big, fmin(big, cy_max))) + 1;
-  const int bx_hi = __double2int_rd(fmax(-big, fmin(big, cx_max))) + 1;
+  const int by_hi = __double2int_rd(fmax(-big, fmin(big, cy_max))) + 2;
+  const int bx_hi = __double2int_rd(fmax(-big, fmin(big, cx_max))) + 2;
   const bool brick_ok = (by_hi - by0) < g.BY && (bx_hi - bx0) < g.BX;  // CTA-uniform
+  if (!brick_ok) {
+    zsep_tile_from_global<T, ORDER, BOUNDARY, SCRUB>(p, y0, x0, zb, ze);
+    return;
+  }
 
   if (tid == 0) {
 #pragma unroll
@@ -102,41 +127,39 @@ __global__ void __launch_bounds__(kZsThreads)
     }
     fence_mbar_init();
   }
+  if (tid < nz) {
+    const double cz = __dadd_rn(p.m[3], __dmul_rn(static_cast<double>(zb + tid + p.cz), p.m[0]));
+    const AxisTap tz = resolve_axis<ORDER, BOUNDARY>(cz, p.sz);
+    int4 e;
+    e.x = tz.inside ? tz.i0 : -1;
+    e.y = tz.i1;
+    e.z = __float_as_int(__fsub_rn(1.0f, tz.w));
+    e.w = __float_as_int(tz.w);
+    ztab[tid] = e;
+  }
   __syncthreads();
 
-  const double m00 = p.m[0], t0 = p.m[3];
-
   if (tid >= kZsConsumers) {
-    // ================= producer warp: all lanes walk the plane sequence, lane 0 issues =================
-    if (brick_ok) {
-      const bool issuer = (tid == kZsConsumers);
-      int s_last = INT_MIN;
-      uint32_t seq = 0;
-      for (int z = zb; z < ze; ++z) {
-        const double cz = __dadd_rn(t0, __dmul_rn(static_cast<double>(z + p.cz), m00));
-        const AxisTap tz = resolve_axis<ORDER, BOUNDARY>(cz, p.sz);
-        if (!tz.inside) continue;
+    // ============ producer warp: walks the plane sequence, lane 0 issues the TMA loads ============
+    const bool issuer = (tid == kZsConsumers);
+    int s_last = INT_MIN;
+    uint32_t seq = 0;
+    for (int zl = 0; zl < nz; ++zl) {
+      const int4 e = ztab[zl];
+      if (e.x < 0) continue;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int s = h ? tz.i1 : tz.i0;
-          if (s > s_last) {
-            const uint32_t stage = seq % kZsStages;
-            if (!(g.debug & 1)) {
-              if (seq >= kZsStages && !(g.debug & 2))
-                mbar_wait(&empty_bar[stage], ((seq / kZsStages) - 1) & 1);
-              if (issuer) {
-                if (g.debug & 4) {
-                  mbar_arrive(&full_bar[stage]);
-                } else {
-                  mbar_expect_tx(&full_bar[stage], static_cast<uint32_t>(g.BY) * g.BX * sizeof(T));
-                  tma_load_3d(stage0 + stage * g.stage_bytes, &src_map, &full_bar[stage], bx0, by0, s);
-                }
-              }
-              __syncwarp();
-            }
-            s_last = s;
-            ++seq;
+      for (int h = 0; h < 2; ++h) {
+        const int s = h ? e.y : e.x;
+        if (s > s_last) {
+          const uint32_t stage = seq % kZsStages;
+          if (seq >= kZsStages) mbar_wait(&empty_bar[stage], ((seq / kZsStages) - 1) & 1);
+          if (issuer) {
+            mbar_expect_tx(&full_bar[stage], static_cast<uint32_t>(g.BY) * g.BX * sizeof(T));
+            tma_load_3d(stage0 + stage * g.stage_bytes, &src_map, &full_bar[stage], bx0, by0, s);
           }
+          __syncwarp();
+          s_last = s;
+          ++seq;
         }
       }
     }
@@ -144,38 +167,38 @@ __global__ void __launch_bounds__(kZsThreads)
   }
 
   // ================================= consumer threads =================================
-  const T* __restrict__ src = static_cast<const T*>(p.src);
   const int lx = tid % kZsTX;
   const int ly = tid / kZsTX;
   const int x = x0 + lx;
+  const uint32_t pitch = static_cast<uint32_t>(g.BX) * sizeof(T);
 
-  int off00[kZsPPT], off01[kZsPPT], off10[kZsPPT], off11[kZsPPT];
-  float wy[kZsPPT], wx[kZsPPT];
-  bool live[kZsPPT];   // point is a real output voxel
-  bool inyx[kZsPPT];   // ... and its in-plane coordinate is inside the source
+  uint32_t off[kZsPPT];  // byte offset of tap (i0y, i0x) inside a stage
+  float w00[kZsPPT], w01[kZsPPT], w10[kZsPPT], w11[kZsPPT];
+  int ooff[kZsPPT];  // output offset relative to the tile origin, -1 = no voxel
+  uint32_t inmask = 0;  // bit i: point i samples inside the source
 #pragma unroll
   for (int i = 0; i < kZsPPT; ++i) {
-    const int y = y0 + ly + kZsRowsPerPass * i;
-    live[i] = (y < p.oy) && (x < p.ox);
+    const int yy = ly + kZsRowsPerPass * i;
+    const int y = y0 + yy;
+    const bool live = (y < p.oy) && (x < p.ox);
     const double yf = static_cast<double>(y + p.cy);
     const double xf = static_cast<double>(x + p.cx);
     const AxisTap ty = resolve_axis<ORDER, BOUNDARY>(coord_yx(yf, xf, p.m + 4), p.sy);
     const AxisTap tx = resolve_axis<ORDER, BOUNDARY>(coord_yx(yf, xf, p.m + 8), p.sx);
-    inyx[i] = live[i] && ty.inside && tx.inside;
-    wy[i] = ty.w;
-    wx[i] = tx.w;
-    if (brick_ok) {
-      off00[i] = (ty.i0 - by0) * g.BX + (tx.i0 - bx0);
-      off01[i] = (ty.i0 - by0) * g.BX + (tx.i1 - bx0);
-      off10[i] = (ty.i1 - by0) * g.BX + (tx.i0 - bx0);
-      off11[i] = (ty.i1 - by0) * g.BX + (tx.i1 - bx0);
-    } else {  // element offsets into a global source plane instead
-      off00[i] = ty.i0 * p.sx + tx.i0;
-      off01[i] = ty.i0 * p.sx + tx.i1;
-      off10[i] = ty.i1 * p.sx + tx.i0;
-      off11[i] = ty.i1 * p.sx + tx.i1;
-    }
-    if (!inyx[i]) off00[i] = off01[i] = off10[i] = off11[i] = 0;
+    const bool in = live && ty.inside && tx.inside;
+    ooff[i] = live ? yy * p.ox + lx : -1;
+    inmask |= in ? (1u << i) : 0u;
+    off[i] = in ? static_cast<uint32_t>(ty.i0 - by0) * pitch +
+                      static_cast<uint32_t>(tx.i0 - bx0) * static_cast<uint32_t>(sizeof(T))
+                : 0u;
+    // bilinear weights; a dropped / clamped neighbour has weight 0 (resolve_axis), so the
+    // neighbour taps can always be read at +1 element / +1 row
+    const float ay = ty.w, ax = tx.w;
+    const float by = __fsub_rn(1.0f, ay), bx = __fsub_rn(1.0f, ax);
+    w00[i] = in ? __fmul_rn(by, bx) : 0.0f;
+    w01[i] = in ? __fmul_rn(by, ax) : 0.0f;
+    w10[i] = in ? __fmul_rn(ay, bx) : 0.0f;
+    w11[i] = in ? __fmul_rn(ay, ax) : 0.0f;
   }
 
   float p_prev[kZsPPT], p_last[kZsPPT];
@@ -183,84 +206,70 @@ __global__ void __launch_bounds__(kZsThreads)
   for (int i = 0; i < kZsPPT; ++i) p_prev[i] = p_last[i] = 0.0f;
   int s_last = INT_MIN;
   uint32_t seq = 0;
-  const int64_t sxy = static_cast<int64_t>(p.sy) * p.sx;
+  const int64_t plane_out = static_cast<int64_t>(p.oy) * p.ox;
+  float* __restrict__ out_tile =
+      p.dst + static_cast<int64_t>(zb) * plane_out + static_cast<int64_t>(y0) * p.ox + x0;
 
-  for (int z = zb; z < ze; ++z) {
-    const double cz = __dadd_rn(t0, __dmul_rn(static_cast<double>(z + p.cz), m00));
-    const AxisTap tz = resolve_axis<ORDER, BOUNDARY>(cz, p.sz);
-    float* __restrict__ out_plane = p.dst + static_cast<int64_t>(z) * p.oy * p.ox;
-    if (!tz.inside) {
+  for (int zl = 0; zl < nz; ++zl, out_tile += plane_out) {
+    const int4 e = ztab[zl];
+    if (e.x < 0) {  // this output plane maps outside the source: zeros
 #pragma unroll
-      for (int i = 0; i < kZsPPT; ++i) {
-        const int y = y0 + ly + kZsRowsPerPass * i;
-        if (live[i]) st_global_cs(out_plane + static_cast<int64_t>(y) * p.ox + x, 0.0f);
-      }
+      for (int i = 0; i < kZsPPT; ++i)
+        if (ooff[i] >= 0) st_global_cs(out_tile + ooff[i], 0.0f);
       continue;
     }
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      const int s = h ? tz.i1 : tz.i0;
+      const int s = h ? e.y : e.x;
       if (s > s_last) {  // CTA-uniform: the next plane of the producer's sequence
-        uint32_t base = 0;
-        const T* gplane = nullptr;
         const uint32_t stage = seq % kZsStages;
-        if (brick_ok) {
-          if (!(g.debug & 1)) mbar_wait(&full_bar[stage], (seq / kZsStages) & 1);
-          base = stage0 + stage * g.stage_bytes;
-        } else {
-          gplane = src + s * sxy;
-        }
+        mbar_wait(&full_bar[stage], (seq / kZsStages) & 1);
+        const uint32_t base = stage0 + stage * g.stage_bytes;
 #pragma unroll
         for (int i = 0; i < kZsPPT; ++i) {
-          p_prev[i] = p_last[i];
-          float v = 0.0f;
-          if (inyx[i]) {
-            float v00, v01, v10, v11;
-            if (brick_ok) {
-              v00 = lds_elem<T>(base, off00[i]);
-              if (ORDER == 1) {
-                v01 = lds_elem<T>(base, off01[i]);
-                v10 = lds_elem<T>(base, off10[i]);
-                v11 = lds_elem<T>(base, off11[i]);
-              }
-            } else {
-              v00 = to_f32<T>(__ldg(gplane + off00[i]));
-              if (ORDER == 1) {
-                v01 = to_f32<T>(__ldg(gplane + off01[i]));
-                v10 = to_f32<T>(__ldg(gplane + off10[i]));
-                v11 = to_f32<T>(__ldg(gplane + off11[i]));
-              }
-            }
-            if (ORDER == 0) {
-              v = (SCRUB && sizeof(T) == 4) ? scrub_value(v00) : v00;
-            } else {
-              v = lerp_w(lerp_w(v00, v01, wx[i]), lerp_w(v10, v11, wx[i]), wy[i]);
-              if (SCRUB && sizeof(T) == 4 && !(fabsf(v) <= FLT_MAX)) {
-                // a NaN/inf tap was involved (possibly with zero weight): redo with the scrub
-                v = lerp_w(lerp_w(scrub_value(v00), scrub_value(v01), wx[i]),
-                           lerp_w(scrub_value(v10), scrub_value(v11), wx[i]), wy[i]);
-              }
+          const uint32_t a0 = base + off[i];
+          float v;
+          if (ORDER == 0) {
+            v = lds_elem<T>(a0);
+            if (SCRUB && sizeof(T) == 4) v = scrub_value(v);
+            v = __fmul_rn(v, w00[i]);  // w00 is 1 inside, 0 outside
+          } else {
+            const uint32_t a1 = a0 + pitch;
+            const float v00 = lds_elem<T>(a0);
+            const float v01 = lds_elem<T>(a0 + sizeof(T));
+            const float v10 = lds_elem<T>(a1);
+            const float v11 = lds_elem<T>(a1 + sizeof(T));
+            v = __fmaf_rn(w11[i], v11,
+                          __fmaf_rn(w10[i], v10, __fmaf_rn(w01[i], v01, __fmul_rn(w00[i], v00))));
+            if (SCRUB && sizeof(T) == 4 && !(fabsf(v) <= FLT_MAX)) {
+              // a NaN/inf tap was involved (possibly with zero weight): redo with the scrub
+              v = __fmaf_rn(w11[i], scrub_value(v11),
+                            __fmaf_rn(w10[i], scrub_value(v10),
+                                      __fmaf_rn(w01[i], scrub_value(v01),
+                                                __fmul_rn(w00[i], scrub_value(v00)))));
             }
           }
+          // un-scrubbed float sources may hold NaN at the dummy tap of an outside point
+          if (sizeof(T) == 4 && !SCRUB && !((inmask >> i) & 1u)) v = 0.0f;
+          p_prev[i] = p_last[i];
           p_last[i] = v;
         }
-        if (brick_ok && !(g.debug & 3)) {
-          __syncwarp();
-          if ((tid & 31) == 0) mbar_arrive(&empty_bar[stage]);
-        }
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(&empty_bar[stage]);
         s_last = s;
         ++seq;
       }
     }
-    const bool first_is_last = (tz.i0 == s_last);
+    if (ORDER == 0 || e.x == s_last) {  // single plane (nearest, or the +1 plane was clamped away)
 #pragma unroll
-    for (int i = 0; i < kZsPPT; ++i) {
-      const int y = y0 + ly + kZsRowsPerPass * i;
-      if (live[i]) {
-        const float v0 = first_is_last ? p_last[i] : p_prev[i];
-        const float v = (ORDER == 0) ? v0 : lerp_w(v0, p_last[i], tz.w);
-        st_global_cs(out_plane + static_cast<int64_t>(y) * p.ox + x, v);
-      }
+      for (int i = 0; i < kZsPPT; ++i)
+        if (ooff[i] >= 0) st_global_cs(out_tile + ooff[i], p_last[i]);
+    } else {
+      const float wz0 = __int_as_float(e.z), wz1 = __int_as_float(e.w);
+#pragma unroll
+      for (int i = 0; i < kZsPPT; ++i)
+        if (ooff[i] >= 0)
+          st_global_cs(out_tile + ooff[i], __fmaf_rn(wz1, p_last[i], __fmul_rn(wz0, p_prev[i])));
     }
   }
 }
@@ -277,15 +286,21 @@ static bool zsep_geometry(const AffineParams& p, ZsepGeom* g, size_t* smem_bytes
   if ((static_cast<int64_t>(p.sx) * sizeof(T)) % 16 != 0) return false;
   const double ey = fabs(m[5]) * (kZsTY - 1) + fabs(m[6]) * (kZsTX - 1);
   const double ex = fabs(m[9]) * (kZsTY - 1) + fabs(m[10]) * (kZsTX - 1);
-  if (!(ey < 250.0) || !(ex < 250.0)) return false;
+  if (!(ey < 240.0) || !(ex < 240.0)) return false;
   const int vec = 16 / sizeof(T);
-  int BY = static_cast<int>(ey) + 4;
-  int BX = static_cast<int>(ex) + 4 + (vec - 1);  // + alignment slack of the brick origin
+  const int BY = static_cast<int>(ey) + 5;
+  int BX = static_cast<int>(ex) + 5 + (vec - 1);  // + alignment slack of the brick origin
   BX = (BX + vec - 1) / vec * vec;
+  // a row pitch that is a multiple of 32 banks keeps the lanes of a warp (which walk along x
+  // and change row every few lanes under rotation) on distinct banks; take it when it fits
+  const int bank_elems = 128 / static_cast<int>(sizeof(T));
+  const int BX_banked = (BX + bank_elems - 1) / bank_elems * bank_elems;
+  auto stage_of = [&](int bx) { return (BY * bx * static_cast<int>(sizeof(T)) + 127) / 128 * 128; };
+  if (BX_banked <= 256 && stage_of(BX_banked) * kZsStages <= 56 * 1024) BX = BX_banked;
   if (BY > 256 || BX > 256) return false;
-  const int stage = (BY * BX * static_cast<int>(sizeof(T)) + 127) / 128 * 128;
+  const int stage = stage_of(BX);
   if (stage * kZsStages > 96 * 1024) return false;
-  if (static_cast<int64_t>(p.sy) * p.sx >= (1LL << 31)) return false;  // int32 fallback offsets
+  if (static_cast<int64_t>(kZsTY) * p.ox >= (1LL << 31)) return false;
   g->BY = BY;
   g->BX = BX;
   g->stage_bytes = stage;
@@ -327,14 +342,12 @@ static int launch_zsep(const AffineParams& p, ZsepGeom g, size_t smem_bytes, cud
   if (tiles < target) zsplit = static_cast<int>((target + tiles - 1) / tiles);
   int zchunk = (p.oz + zsplit - 1) / zsplit;
   if (zchunk < 8) zchunk = 8;
+  if (zchunk > kZsMaxChunk) zchunk = kZsMaxChunk;
   if (zchunk > p.oz) zchunk = p.oz;
   g.zchunk = zchunk;
-  {
-    const char* dbg = getenv("B2_ZSEP_DEBUG");
-    g.debug = dbg ? atoi(dbg) : 0;
-  }
   const int grid_z = (p.oz + zchunk - 1) / zchunk;
-  if (tiles_y > 65535 || grid_z > 65535) return affine_gather_launch(p, sizeof(T) == 2 ? 0 : 1, stream);
+  if (tiles_y > 65535 || grid_z > 65535)
+    return affine_gather_launch(p, sizeof(T) == 2 ? B2_DTYPE_U16 : B2_DTYPE_F32, stream);
 
   auto kern = affine_zsep_kernel<T, ORDER, BOUNDARY, SCRUB>;
   B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -346,6 +359,20 @@ static int launch_zsep(const AffineParams& p, ZsepGeom g, size_t smem_bytes, cud
   return B2_OK;
 }
 
+// identity linear part with an integer translation: linear interpolation degenerates to a
+// shifted copy, which the nearest-neighbour instantiation performs bit-exactly with 1 tap
+static bool is_integer_translation(const AffineParams& p) {
+  const double* m = p.m;
+  const bool ident = m[0] == 1.0 && m[1] == 0.0 && m[2] == 0.0 && m[4] == 0.0 && m[5] == 1.0 &&
+                     m[6] == 0.0 && m[8] == 0.0 && m[9] == 0.0 && m[10] == 1.0;
+  if (!ident) return false;
+  for (int d = 0; d < 3; ++d) {
+    const double t = m[4 * d + 3];
+    if (fabs(t) > 1e9 || t != static_cast<double>(static_cast<long long>(t))) return false;
+  }
+  return true;
+}
+
 template <typename T>
 static int zsep_typed(const AffineParams& p, cudaStream_t stream, bool* eligible) {
   ZsepGeom g{};
@@ -353,10 +380,11 @@ static int zsep_typed(const AffineParams& p, cudaStream_t stream, bool* eligible
   *eligible = zsep_geometry<T>(p, &g, &smem);
   if (!*eligible) return B2_ERR_UNSUPPORTED;
   const bool scrub = p.scrub && sizeof(T) == 4;
-#define B2_ZS(ORD, BND)                                                          \
-  (scrub ? launch_zsep<T, ORD, BND, true>(p, g, smem, stream)                    \
+  const int order = (p.order == 1 && is_integer_translation(p)) ? 0 : p.order;
+#define B2_ZS(ORD, BND)                                       \
+  (scrub ? launch_zsep<T, ORD, BND, true>(p, g, smem, stream) \
          : launch_zsep<T, ORD, BND, false>(p, g, smem, stream))
-  if (p.order == 0)
+  if (order == 0)
     return p.boundary == B2_BOUNDARY_CONSTANT ? B2_ZS(0, B2_BOUNDARY_CONSTANT)
                                               : B2_ZS(0, B2_BOUNDARY_ITK);
   return p.boundary == B2_BOUNDARY_CONSTANT ? B2_ZS(1, B2_BOUNDARY_CONSTANT)

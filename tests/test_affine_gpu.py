@@ -104,7 +104,7 @@ def test_tma_path_is_taken_and_matches_gather(mname):
             if order == 0:
                 assert torch.equal(a, b)
             else:
-                assert (a - b).abs().max().item() <= 1e-6 * 4095.0
+                assert (a - b).abs().max().item() <= 2e-6 * 4095.0  # 4-weight vs nested-lerp rounding
 
 
 def test_generic_matrix_not_tma_eligible():
