@@ -1,17 +1,23 @@
 // Host-buffer pipeline behind b2h_deskew / b2h_affine3d: numpy-in / numpy-out callers
 // (reference biahub/deskew.py:551-579, biahub/register.py:202-281, biahub/stabilize.py:32-90)
-// hand over pageable or pinned HOST arrays; the source volume is made resident in HBM, resampled
-// slab by slab and copied back while later slabs are still being computed.
+// hand over pageable or pinned HOST arrays and get a complete HOST result back.
 //
-//   upload  stream : chunked cudaMemcpyAsync H2D (one call per chunk; pageable sources are first
-//                    copied into a pinned staging buffer by a small pool of host threads)
-//   compute stream : one kernel launch per output slab, ordered after the chunks it needs
-//   download stream: cudaMemcpyAsync D2H of each finished slab, un-staged by the host pool
+// The output volume is cut into slabs along its slowest axis.  Slab i needs only a band of the
+// source (deskew: a band of tilt rows of every scan plane; affine: a range of source planes), so
 //
-// Per-process, per-device state (streams, pinned and device buffers) is cached and grown on
-// demand; b2h_release() frees it.
+//   upload   stream: H2D of the source band of slab i+1        (cudaMemcpy2DAsync / cudaMemcpyAsync,
+//                                                                one call per band - never batched)
+//   compute  stream: resampling kernel of slab i                (ordered after its band by an event)
+//   download stream: D2H of slab i-1                            (ordered after its kernel by an event)
+//
+// run concurrently: PCIe carries traffic in both directions at once and the kernel time hides
+// behind the copies.  Pinned user buffers are used directly; pageable ones are staged through
+// small pinned rings by a pool of host threads.  Per-process, per-device state (streams, device
+// volumes, pinned rings, events) is cached and grown on demand; b2h_release() frees it.
 #include <algorithm>
+#include <condition_variable>
 #include <cstring>
+#include <functional>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -29,9 +35,123 @@ int affine_device(const void* src, int src_dtype, int64_t sz, int64_t sy, int64_
 
 namespace {
 
-constexpr size_t kChunkBytes = 32u << 20;  // granularity of the copy pipeline
+constexpr size_t kSlabBytes = 48u << 20;  // target output bytes per slab
+constexpr int kRing = 3;                  // pinned staging ring depth (pageable callers)
 constexpr int kMaxDevices = 16;
 
+// ------------------------------------------------------------------ host thread pool
+class HostPool {
+ public:
+  static HostPool& get() {
+    static HostPool pool;
+    return pool;
+  }
+  int size() const { return static_cast<int>(workers_.size()) + 1; }
+
+  // run fn(i) for i in [0, n) on the pool + the calling thread; returns when all are done
+  void parallel_for(int n, const std::function<void(int)>& fn) {
+    if (n <= 0) return;
+    if (n == 1 || workers_.empty()) {
+      for (int i = 0; i < n; ++i) fn(i);
+      return;
+    }
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      fn_ = &fn;
+      next_ = 0;
+      total_ = n;
+      pending_ = n;
+      ++epoch_;
+    }
+    cv_.notify_all();
+    work();
+    std::unique_lock<std::mutex> lk(mu_);
+    done_cv_.wait(lk, [&] { return pending_ == 0; });
+    fn_ = nullptr;
+  }
+
+ private:
+  HostPool() {
+    unsigned hc = std::thread::hardware_concurrency();
+    int t = hc ? static_cast<int>(hc) : 4;
+    const char* env = getenv("B2_HOST_THREADS");
+    if (env && atoi(env) > 0) t = atoi(env);
+    t = std::max(1, std::min(t, 12));
+    for (int i = 1; i < t; ++i) workers_.emplace_back([this] { loop(); });
+  }
+  ~HostPool() {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      stop_ = true;
+    }
+    cv_.notify_all();
+    for (auto& w : workers_) w.join();
+  }
+  void work() {
+    for (;;) {
+      int i;
+      const std::function<void(int)>* fn;
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        if (!fn_ || next_ >= total_) return;
+        i = next_++;
+        fn = fn_;
+      }
+      (*fn)(i);
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        if (--pending_ == 0) done_cv_.notify_all();
+      }
+    }
+  }
+  void loop() {
+    uint64_t seen = 0;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return stop_ || epoch_ != seen; });
+        if (stop_) return;
+        seen = epoch_;
+      }
+      work();
+    }
+  }
+  std::vector<std::thread> workers_;
+  std::mutex mu_;
+  std::condition_variable cv_, done_cv_;
+  const std::function<void(int)>* fn_ = nullptr;
+  int next_ = 0, total_ = 0, pending_ = 0;
+  uint64_t epoch_ = 0;
+  bool stop_ = false;
+};
+
+// copy `rows` rows of `width` bytes between pitched host buffers, split over the pool
+void host_copy_2d(char* dst, size_t dpitch, const char* src, size_t spitch, size_t width,
+                  size_t rows) {
+  HostPool& pool = HostPool::get();
+  const size_t total = width * rows;
+  int parts = static_cast<int>(std::min<size_t>(pool.size(), std::max<size_t>(1, total >> 21)));
+  if (parts <= 1) {
+    for (size_t r = 0; r < rows; ++r) memcpy(dst + r * dpitch, src + r * spitch, width);
+    return;
+  }
+  if (rows >= static_cast<size_t>(parts)) {
+    pool.parallel_for(parts, [&](int t) {
+      const size_t r0 = rows * t / parts, r1 = rows * (t + 1) / parts;
+      for (size_t r = r0; r < r1; ++r) memcpy(dst + r * dpitch, src + r * spitch, width);
+    });
+  } else {  // few long rows: split each row
+    for (size_t r = 0; r < rows; ++r) {
+      pool.parallel_for(parts, [&](int t) {
+        const size_t b0 = (width * t / parts) & ~static_cast<size_t>(63);
+        const size_t b1 = (t + 1 == parts) ? width : ((width * (t + 1) / parts) & ~static_cast<size_t>(63));
+        memcpy(dst + r * dpitch + b0, src + r * spitch + b0, b1 - b0);
+      });
+    }
+  }
+}
+
+// ------------------------------------------------------------------ per-device context
 struct DeviceCtx {
   bool init = false;
   cudaStream_t s_up = nullptr, s_run = nullptr, s_down = nullptr;
@@ -39,44 +159,15 @@ struct DeviceCtx {
   size_t d_src_bytes = 0;
   void* d_dst = nullptr;
   size_t d_dst_bytes = 0;
-  void* h_in = nullptr;  // pinned staging
-  size_t h_in_bytes = 0;
-  void* h_out = nullptr;
-  size_t h_out_bytes = 0;
+  void* h_in[kRing] = {nullptr, nullptr, nullptr};
+  size_t h_in_bytes[kRing] = {0, 0, 0};
+  void* h_out[kRing] = {nullptr, nullptr, nullptr};
+  size_t h_out_bytes[kRing] = {0, 0, 0};
   std::vector<cudaEvent_t> events;
 };
 
 std::mutex g_mu;  // b2h_* calls are serialised per process (one worker process per GPU)
 DeviceCtx g_ctx[kMaxDevices];
-
-int host_threads() {
-  static int n = [] {
-    unsigned hc = std::thread::hardware_concurrency();
-    int t = hc ? static_cast<int>(hc) : 4;
-    const char* env = getenv("B2_HOST_THREADS");
-    if (env && atoi(env) > 0) t = atoi(env);
-    return std::max(1, std::min(t, 16));
-  }();
-  return n;
-}
-
-// memcpy split over a few threads (pageable <-> pinned staging runs at memory speed this way)
-void parallel_memcpy(void* dst, const void* src, size_t bytes) {
-  const int nt = host_threads();
-  if (bytes < (8u << 20) || nt == 1) {
-    memcpy(dst, src, bytes);
-    return;
-  }
-  std::vector<std::thread> th;
-  const size_t per = (bytes / nt + 4095) & ~static_cast<size_t>(4095);
-  for (int t = 0; t < nt; ++t) {
-    const size_t off = static_cast<size_t>(t) * per;
-    if (off >= bytes) break;
-    const size_t len = std::min(per, bytes - off);
-    th.emplace_back([=] { memcpy(static_cast<char*>(dst) + off, static_cast<const char*>(src) + off, len); });
-  }
-  for (auto& t : th) t.join();
-}
 
 bool is_pinned(const void* p) {
   cudaPointerAttributes a;
@@ -134,62 +225,106 @@ int get_event(DeviceCtx& c, size_t i, cudaEvent_t* ev) {
   return B2_OK;
 }
 
-// H2D of `bytes` in chunks; returns after everything is ENQUEUED on c.s_up (pageable sources
-// have been staged by then).  `ready` is recorded on s_up after the last chunk.
-int upload(DeviceCtx& c, void* d_dst, const void* h_src, size_t bytes, cudaEvent_t ready) {
-  const bool direct = is_pinned(h_src);
-  if (!direct) {
-    int rc = grow_pinned(&c.h_in, &c.h_in_bytes, bytes);
-    if (rc) return rc;
-  }
-  for (size_t off = 0; off < bytes; off += kChunkBytes) {
-    const size_t len = std::min(kChunkBytes, bytes - off);
-    const char* from = static_cast<const char*>(h_src) + off;
-    if (!direct) {
-      parallel_memcpy(static_cast<char*>(c.h_in) + off, from, len);
-      from = static_cast<const char*>(c.h_in) + off;
-    }
-    B2_CUDA(cudaMemcpyAsync(static_cast<char*>(d_dst) + off, from, len, cudaMemcpyHostToDevice,
-                            c.s_up));
-  }
-  B2_CUDA(cudaEventRecord(ready, c.s_up));
-  return B2_OK;
-}
-
-// D2H of `bytes` (already ordered after the producing kernel on s_down); blocks until complete.
-int download(DeviceCtx& c, void* h_dst, const void* d_src, size_t bytes, size_t ev_base) {
-  const bool direct = is_pinned(h_dst);
-  if (!direct) {
-    int rc = grow_pinned(&c.h_out, &c.h_out_bytes, bytes);
-    if (rc) return rc;
-  }
-  const size_t nchunks = (bytes + kChunkBytes - 1) / kChunkBytes;
-  for (size_t i = 0; i < nchunks; ++i) {
-    const size_t off = i * kChunkBytes;
-    const size_t len = std::min(kChunkBytes, bytes - off);
-    char* to = direct ? static_cast<char*>(h_dst) + off : static_cast<char*>(c.h_out) + off;
-    B2_CUDA(cudaMemcpyAsync(to, static_cast<const char*>(d_src) + off, len, cudaMemcpyDeviceToHost,
-                            c.s_down));
-    cudaEvent_t ev;
-    int rc = get_event(c, ev_base + i, &ev);
-    if (rc) return rc;
-    B2_CUDA(cudaEventRecord(ev, c.s_down));
-  }
-  for (size_t i = 0; i < nchunks; ++i) {
-    cudaEvent_t ev;
-    int rc = get_event(c, ev_base + i, &ev);
-    if (rc) return rc;
-    B2_CUDA(cudaEventSynchronize(ev));
-    if (!direct) {
-      const size_t off = i * kChunkBytes;
-      const size_t len = std::min(kChunkBytes, bytes - off);
-      parallel_memcpy(static_cast<char*>(h_dst) + off, static_cast<char*>(c.h_out) + off, len);
-    }
-  }
-  return B2_OK;
-}
-
 size_t elem_size(int dtype) { return dtype == B2_DTYPE_U16 ? 2 : 4; }
+
+// A band of the source: `rows` pieces of `width` bytes, piece r at byte offset off + r*pitch of
+// both the host volume and its device mirror.
+struct Band {
+  size_t off = 0, pitch = 0, width = 0, rows = 0;
+  size_t bytes() const { return width * rows; }
+};
+
+struct Slab {
+  std::vector<Band> bands;  // source data to upload before this slab's kernel
+  size_t out_off = 0, out_bytes = 0;
+  std::function<int(cudaStream_t)> launch;
+};
+
+// Run the three-stream pipeline over `slabs`.
+int run_pipeline(DeviceCtx& c, const char* h_src, char* h_dst, std::vector<Slab>& slabs) {
+  const bool src_pinned = is_pinned(h_src);
+  const bool dst_pinned = is_pinned(h_dst);
+  const size_t S = slabs.size();
+  auto ev = [&](size_t kind, size_t i, cudaEvent_t* e) { return get_event(c, 3 * i + kind, e); };
+  int rc;
+
+  auto unstage = [&](size_t j) -> int {
+    cudaEvent_t e;
+    if ((rc = ev(2, j, &e))) return rc;
+    B2_CUDA(cudaEventSynchronize(e));
+    host_copy_2d(h_dst + slabs[j].out_off, slabs[j].out_bytes,
+                 static_cast<const char*>(c.h_out[j % kRing]), slabs[j].out_bytes,
+                 slabs[j].out_bytes, 1);
+    return B2_OK;
+  };
+
+  for (size_t i = 0; i < S; ++i) {
+    Slab& sl = slabs[i];
+    cudaEvent_t e_up, e_run, e_down;
+    if ((rc = ev(0, i, &e_up)) || (rc = ev(1, i, &e_run)) || (rc = ev(2, i, &e_down))) return rc;
+
+    // ---- upload the source band(s) of this slab
+    size_t band_total = 0;
+    for (const Band& b : sl.bands) band_total += b.bytes();
+    if (!src_pinned && band_total) {
+      if (i >= static_cast<size_t>(kRing)) {  // ring slot reuse: its previous upload must be done
+        cudaEvent_t prev;
+        if ((rc = ev(0, i - kRing, &prev))) return rc;
+        B2_CUDA(cudaEventSynchronize(prev));
+      }
+      if ((rc = grow_pinned(&c.h_in[i % kRing], &c.h_in_bytes[i % kRing], band_total))) return rc;
+    }
+    size_t stage_off = 0;
+    for (const Band& b : sl.bands) {
+      if (!b.bytes()) continue;
+      char* d = static_cast<char*>(c.d_src) + b.off;
+      if (src_pinned) {
+        if (b.rows == 1)
+          B2_CUDA(cudaMemcpyAsync(d, h_src + b.off, b.width, cudaMemcpyHostToDevice, c.s_up));
+        else
+          B2_CUDA(cudaMemcpy2DAsync(d, b.pitch, h_src + b.off, b.pitch, b.width, b.rows,
+                                    cudaMemcpyHostToDevice, c.s_up));
+      } else {
+        char* st = static_cast<char*>(c.h_in[i % kRing]) + stage_off;
+        host_copy_2d(st, b.width, h_src + b.off, b.pitch, b.width, b.rows);
+        if (b.rows == 1)
+          B2_CUDA(cudaMemcpyAsync(d, st, b.width, cudaMemcpyHostToDevice, c.s_up));
+        else
+          B2_CUDA(cudaMemcpy2DAsync(d, b.pitch, st, b.width, b.width, b.rows,
+                                    cudaMemcpyHostToDevice, c.s_up));
+        stage_off += b.bytes();
+      }
+    }
+    B2_CUDA(cudaEventRecord(e_up, c.s_up));
+
+    // ---- kernel of this slab
+    B2_CUDA(cudaStreamWaitEvent(c.s_run, e_up, 0));
+    if ((rc = sl.launch(c.s_run))) return rc;
+    B2_CUDA(cudaEventRecord(e_run, c.s_run));
+
+    // ---- download
+    B2_CUDA(cudaStreamWaitEvent(c.s_down, e_run, 0));
+    const char* d_out = static_cast<const char*>(c.d_dst) + sl.out_off;
+    if (dst_pinned) {
+      B2_CUDA(cudaMemcpyAsync(h_dst + sl.out_off, d_out, sl.out_bytes, cudaMemcpyDeviceToHost,
+                              c.s_down));
+    } else {
+      if (i >= static_cast<size_t>(kRing) && (rc = unstage(i - kRing))) return rc;
+      if ((rc = grow_pinned(&c.h_out[i % kRing], &c.h_out_bytes[i % kRing], sl.out_bytes)))
+        return rc;
+      B2_CUDA(cudaMemcpyAsync(c.h_out[i % kRing], d_out, sl.out_bytes, cudaMemcpyDeviceToHost,
+                              c.s_down));
+    }
+    B2_CUDA(cudaEventRecord(e_down, c.s_down));
+  }
+  if (!dst_pinned) {
+    for (size_t j = (S > static_cast<size_t>(kRing) ? S - kRing : 0); j < S; ++j)
+      if ((rc = unstage(j))) return rc;
+  }
+  B2_CUDA(cudaStreamSynchronize(c.s_down));
+  B2_CUDA(cudaStreamSynchronize(c.s_up));
+  return B2_OK;
+}
 
 }  // namespace
 
@@ -204,7 +339,8 @@ int host_deskew(const void* h_src, int src_dtype, int64_t Zi, int64_t Yi, int64_
     set_error("b2h_deskew: unknown src_dtype %d", src_dtype);
     return B2_ERR_INVALID;
   }
-  if (Zi < 1 || Yi < 1 || Xi < 1 || Zavg < 1 || Yo < 1 || Xo < 1) {
+  if (Zi < 2 || Yi < 1 || Xi < 1 || Zavg < 1 || Yo < 1 || Xo < 1 || N < 1 || Zo_full != Yi ||
+      Zavg != (Zo_full + N - 1) / N) {
     set_error("b2h_deskew: invalid shape");
     return B2_ERR_INVALID;
   }
@@ -212,46 +348,41 @@ int host_deskew(const void* h_src, int src_dtype, int64_t Zi, int64_t Yi, int64_
   DeviceCtx* c = nullptr;
   int rc = get_ctx(device, &c);
   if (rc) return rc;
-  const size_t in_bytes = static_cast<size_t>(Zi) * Yi * Xi * elem_size(src_dtype);
+  const size_t es = elem_size(src_dtype);
+  const size_t in_bytes = static_cast<size_t>(Zi) * Yi * Xi * es;
   const size_t out_bytes = static_cast<size_t>(Zavg) * Yo * Xo * sizeof(float);
   if ((rc = grow_device(&c->d_src, &c->d_src_bytes, in_bytes))) return rc;
   if ((rc = grow_device(&c->d_dst, &c->d_dst_bytes, out_bytes))) return rc;
 
-  cudaEvent_t up_done, run_done;
-  if ((rc = get_event(*c, 0, &up_done))) return rc;
-  if ((rc = get_event(*c, 1, &run_done))) return rc;
-  if ((rc = upload(*c, c->d_src, h_src, in_bytes, up_done))) return rc;
-  B2_CUDA(cudaStreamWaitEvent(c->s_run, up_done, 0));
-
-  // output slabs along the averaged-slice axis: each slab is contiguous in dst and can start
-  // its D2H while the next slab is being computed
+  // slabs of averaged slices [a0, a0+cnt): contiguous in dst; they read tilt rows
+  // iy in [Yi - min((a0+cnt)*N, Yi), Yi - 1 - a0*N] of every scan plane
   const size_t slice_bytes = static_cast<size_t>(Yo) * Xo * sizeof(float);
-  int64_t per_slab = std::max<int64_t>(1, static_cast<int64_t>((64u << 20) / slice_bytes));
-  size_t ev_next = 2;
-  std::vector<std::pair<int64_t, int64_t>> slabs;
-  for (int64_t a0 = 0; a0 < Zavg; a0 += per_slab) slabs.emplace_back(a0, std::min(per_slab, Zavg - a0));
-  std::vector<cudaEvent_t> slab_ev(slabs.size());
-  for (size_t i = 0; i < slabs.size(); ++i) {
-    const int slab[4] = {0, static_cast<int>(Yi), static_cast<int>(slabs[i].first),
-                         static_cast<int>(slabs[i].second)};
-    float* d_out = static_cast<float*>(c->d_dst) + slabs[i].first * Yo * Xo;
-    rc = deskew_device(c->d_src, src_dtype, Zi, Yi, Xi, d_out, Zavg, Yo, Xo, Zo_full, N, px32,
-                       pxct32, off32, B2_PATH_AUTO, c->s_run, slab);
-    if (rc) return rc;
-    if ((rc = get_event(*c, ev_next++, &slab_ev[i]))) return rc;
-    B2_CUDA(cudaEventRecord(slab_ev[i], c->s_run));
+  const int64_t per_slab = std::max<int64_t>(1, static_cast<int64_t>(kSlabBytes / slice_bytes));
+  const size_t row_bytes = static_cast<size_t>(Xi) * es;
+  std::vector<Slab> slabs;
+  void* d_src = c->d_src;
+  float* d_dst = static_cast<float*>(c->d_dst);
+  for (int64_t a0 = 0; a0 < Zavg; a0 += per_slab) {
+    const int64_t cnt = std::min(per_slab, Zavg - a0);
+    const int64_t iy_hi = Yi - 1 - a0 * N;
+    const int64_t iy_lo = Yi - std::min<int64_t>((a0 + cnt) * N, Yi);
+    Slab s;
+    Band b;
+    b.off = static_cast<size_t>(iy_lo) * row_bytes;
+    b.pitch = static_cast<size_t>(Yi) * row_bytes;
+    b.width = static_cast<size_t>(iy_hi - iy_lo + 1) * row_bytes;
+    b.rows = static_cast<size_t>(Zi);
+    s.bands.push_back(b);
+    s.out_off = static_cast<size_t>(a0) * slice_bytes;
+    s.out_bytes = static_cast<size_t>(cnt) * slice_bytes;
+    s.launch = [=](cudaStream_t st) {
+      const int slab[4] = {0, static_cast<int>(Yi), static_cast<int>(a0), static_cast<int>(cnt)};
+      return deskew_device(d_src, src_dtype, Zi, Yi, Xi, d_dst + a0 * Yo * Xo, Zavg, Yo, Xo,
+                           Zo_full, N, px32, pxct32, off32, B2_PATH_AUTO, st, slab);
+    };
+    slabs.push_back(std::move(s));
   }
-  (void)run_done;
-  for (size_t i = 0; i < slabs.size(); ++i) {
-    B2_CUDA(cudaStreamWaitEvent(c->s_down, slab_ev[i], 0));
-    const size_t off = static_cast<size_t>(slabs[i].first) * slice_bytes;
-    const size_t len = static_cast<size_t>(slabs[i].second) * slice_bytes;
-    rc = download(*c, reinterpret_cast<char*>(h_dst) + off, static_cast<char*>(c->d_dst) + off, len,
-                  ev_next);
-    if (rc) return rc;
-  }
-  B2_CUDA(cudaStreamSynchronize(c->s_down));
-  return B2_OK;
+  return run_pipeline(*c, static_cast<const char*>(h_src), reinterpret_cast<char*>(h_dst), slabs);
 }
 
 int host_affine(const void* h_src, int src_dtype, int64_t sz, int64_t sy, int64_t sx, float* h_dst,
@@ -274,43 +405,75 @@ int host_affine(const void* h_src, int src_dtype, int64_t sz, int64_t sy, int64_
   DeviceCtx* c = nullptr;
   int rc = get_ctx(device, &c);
   if (rc) return rc;
-  const size_t in_bytes = static_cast<size_t>(sz) * sy * sx * elem_size(src_dtype);
+  const size_t es = elem_size(src_dtype);
+  const size_t plane_in = static_cast<size_t>(sy) * sx * es;
+  const size_t in_bytes = static_cast<size_t>(sz) * plane_in;
   const size_t out_bytes = static_cast<size_t>(oz) * oy * ox * sizeof(float);
   if ((rc = grow_device(&c->d_src, &c->d_src_bytes, in_bytes))) return rc;
   if ((rc = grow_device(&c->d_dst, &c->d_dst_bytes, out_bytes))) return rc;
 
-  cudaEvent_t up_done;
-  if ((rc = get_event(*c, 0, &up_done))) return rc;
-  if ((rc = upload(*c, c->d_src, h_src, in_bytes, up_done))) return rc;
-  B2_CUDA(cudaStreamWaitEvent(c->s_run, up_done, 0));
-
-  const size_t plane_bytes = static_cast<size_t>(oy) * ox * sizeof(float);
-  int64_t per_slab = std::max<int64_t>(1, static_cast<int64_t>((64u << 20) / plane_bytes));
-  size_t ev_next = 1;
-  std::vector<std::pair<int64_t, int64_t>> slabs;
-  for (int64_t z0 = 0; z0 < oz; z0 += per_slab) slabs.emplace_back(z0, std::min(per_slab, oz - z0));
-  std::vector<cudaEvent_t> slab_ev(slabs.size());
-  for (size_t i = 0; i < slabs.size(); ++i) {
-    int64_t crop[3] = {crop_start ? crop_start[0] : 0, crop_start ? crop_start[1] : 0,
-                       crop_start ? crop_start[2] : 0};
-    crop[0] += slabs[i].first;
-    float* d_out = static_cast<float*>(c->d_dst) + slabs[i].first * oy * ox;
-    rc = affine_device(c->d_src, src_dtype, sz, sy, sx, d_out, slabs[i].second, oy, ox, M12, crop,
-                       order, boundary, scrub, B2_PATH_AUTO, c->s_run);
-    if (rc) return rc;
-    if ((rc = get_event(*c, ev_next++, &slab_ev[i]))) return rc;
-    B2_CUDA(cudaEventRecord(slab_ev[i], c->s_run));
+  const int64_t c0[3] = {crop_start ? crop_start[0] : 0, crop_start ? crop_start[1] : 0,
+                         crop_start ? crop_start[2] : 0};
+  const size_t plane_out = static_cast<size_t>(oy) * ox * sizeof(float);
+  const int64_t per_slab = std::max<int64_t>(1, static_cast<int64_t>(kSlabBytes / plane_out));
+  std::vector<Slab> slabs;
+  void* d_src = c->d_src;
+  float* d_dst = static_cast<float*>(c->d_dst);
+  std::vector<double> M(M12, M12 + 12);
+  int64_t up_lo = 0, up_hi = 0;  // source planes [up_lo, up_hi) already scheduled for upload
+  bool any = false;
+  for (int64_t z0 = 0; z0 < oz; z0 += per_slab) {
+    const int64_t cnt = std::min(per_slab, oz - z0);
+    // source plane range touched by this output slab: back-project its 8 corners
+    double lo = 1e300, hi = -1e300;
+    for (int k = 0; k < 8; ++k) {
+      const double z = static_cast<double>((k & 1 ? z0 + cnt - 1 : z0) + c0[0]);
+      const double y = static_cast<double>((k & 2 ? oy - 1 : 0) + c0[1]);
+      const double x = static_cast<double>((k & 4 ? ox - 1 : 0) + c0[2]);
+      const double cz = M[3] + z * M[0] + y * M[1] + x * M[2];
+      lo = std::min(lo, cz);
+      hi = std::max(hi, cz);
+    }
+    int64_t p_lo = static_cast<int64_t>(std::floor(std::max(lo, -1.0e15))) - 1;
+    int64_t p_hi = static_cast<int64_t>(std::floor(std::min(hi, 1.0e15))) + 2;  // inclusive
+    p_lo = std::max<int64_t>(p_lo, 0);
+    p_hi = std::min<int64_t>(p_hi, sz - 1);
+    Slab s;
+    if (p_lo <= p_hi) {
+      auto add = [&](int64_t a, int64_t b) {  // planes [a, b)
+        if (a >= b) return;
+        Band band;
+        band.off = static_cast<size_t>(a) * plane_in;
+        band.pitch = band.width = static_cast<size_t>(b - a) * plane_in;
+        band.rows = 1;
+        s.bands.push_back(band);
+      };
+      if (!any) {
+        add(p_lo, p_hi + 1);
+        up_lo = p_lo;
+        up_hi = p_hi + 1;
+        any = true;
+      } else {
+        if (p_lo < up_lo) {
+          add(p_lo, up_lo);
+          up_lo = p_lo;
+        }
+        if (p_hi + 1 > up_hi) {
+          add(up_hi, p_hi + 1);
+          up_hi = p_hi + 1;
+        }
+      }
+    }
+    s.out_off = static_cast<size_t>(z0) * plane_out;
+    s.out_bytes = static_cast<size_t>(cnt) * plane_out;
+    s.launch = [=](cudaStream_t st) {
+      const int64_t crop[3] = {c0[0] + z0, c0[1], c0[2]};
+      return affine_device(d_src, src_dtype, sz, sy, sx, d_dst + z0 * oy * ox, cnt, oy, ox,
+                           M.data(), crop, order, boundary, scrub, B2_PATH_AUTO, st);
+    };
+    slabs.push_back(std::move(s));
   }
-  for (size_t i = 0; i < slabs.size(); ++i) {
-    B2_CUDA(cudaStreamWaitEvent(c->s_down, slab_ev[i], 0));
-    const size_t off = static_cast<size_t>(slabs[i].first) * plane_bytes;
-    const size_t len = static_cast<size_t>(slabs[i].second) * plane_bytes;
-    rc = download(*c, reinterpret_cast<char*>(h_dst) + off, static_cast<char*>(c->d_dst) + off, len,
-                  ev_next);
-    if (rc) return rc;
-  }
-  B2_CUDA(cudaStreamSynchronize(c->s_down));
-  return B2_OK;
+  return run_pipeline(*c, static_cast<const char*>(h_src), reinterpret_cast<char*>(h_dst), slabs);
 }
 
 int host_release() {
@@ -324,8 +487,10 @@ int host_release() {
     c.events.clear();
     if (c.d_src) cudaFree(c.d_src);
     if (c.d_dst) cudaFree(c.d_dst);
-    if (c.h_in) cudaFreeHost(c.h_in);
-    if (c.h_out) cudaFreeHost(c.h_out);
+    for (int r = 0; r < kRing; ++r) {
+      if (c.h_in[r]) cudaFreeHost(c.h_in[r]);
+      if (c.h_out[r]) cudaFreeHost(c.h_out[r]);
+    }
     cudaStreamDestroy(c.s_up);
     cudaStreamDestroy(c.s_run);
     cudaStreamDestroy(c.s_down);
