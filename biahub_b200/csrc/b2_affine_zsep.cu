@@ -209,67 +209,99 @@ __global__ void __launch_bounds__(kZsThreads, 3)
   const int64_t plane_out = static_cast<int64_t>(p.oy) * p.ox;
   float* __restrict__ out_tile =
       p.dst + static_cast<int64_t>(zb) * plane_out + static_cast<int64_t>(y0) * p.ox + x0;
+  const uint32_t full0 = smem_u32(&full_bar[0]);
+  const uint32_t empty0 = smem_u32(&empty_bar[0]);
+  const bool full_tile = (y0 + kZsTY <= p.oy) && (x0 + kZsTX <= p.ox);  // CTA-uniform
+
+  // reduce the next plane of the producer's sequence to one value per point (p_last)
+  auto fetch_plane = [&]() {
+    const uint32_t stage = seq % kZsStages;
+    mbar_wait_u32(full0 + stage * 8u, (seq / kZsStages) & 1u);
+    const uint32_t base = stage0 + stage * g.stage_bytes;
+    float v[kZsPPT];
+    if (ORDER == 0) {
+#pragma unroll
+      for (int i = 0; i < kZsPPT; ++i) {
+        float t = lds_elem<T>(base + off[i]);
+        if (SCRUB && sizeof(T) == 4) t = scrub_value(t);
+        v[i] = ((inmask >> i) & 1u) ? t : 0.0f;
+      }
+    } else {
+      float t00[kZsPPT], t01[kZsPPT], t10[kZsPPT], t11[kZsPPT];
+#pragma unroll
+      for (int i = 0; i < kZsPPT; ++i) {
+        const uint32_t a0 = base + off[i];
+        const uint32_t a1 = a0 + pitch;
+        t00[i] = lds_elem<T>(a0);
+        t01[i] = lds_elem<T>(a0 + sizeof(T));
+        t10[i] = lds_elem<T>(a1);
+        t11[i] = lds_elem<T>(a1 + sizeof(T));
+      }
+      bool bad = false;
+#pragma unroll
+      for (int i = 0; i < kZsPPT; ++i) {
+        v[i] = __fmaf_rn(w11[i], t11[i],
+                         __fmaf_rn(w10[i], t10[i], __fmaf_rn(w01[i], t01[i], __fmul_rn(w00[i], t00[i]))));
+        bad |= !(fabsf(v[i]) <= FLT_MAX);
+      }
+      if (sizeof(T) == 4 && bad) {
+        // a NaN/inf tap was involved (possibly with zero weight): redo with the scrub
+        // (np.nan_to_num semantics); without SCRUB only the dummy taps of outside points are fixed
+#pragma unroll
+        for (int i = 0; i < kZsPPT; ++i) {
+          if (SCRUB) {
+            v[i] = __fmaf_rn(w11[i], scrub_value(t11[i]),
+                             __fmaf_rn(w10[i], scrub_value(t10[i]),
+                                       __fmaf_rn(w01[i], scrub_value(t01[i]),
+                                                 __fmul_rn(w00[i], scrub_value(t00[i])))));
+          } else if (!((inmask >> i) & 1u)) {
+            v[i] = 0.0f;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < kZsPPT; ++i) {
+      p_prev[i] = p_last[i];
+      p_last[i] = v[i];
+    }
+    __syncwarp();
+    if ((tid & 31) == 0) mbar_arrive_u32(empty0 + stage * 8u);
+    ++seq;
+  };
 
   for (int zl = 0; zl < nz; ++zl, out_tile += plane_out) {
     const int4 e = ztab[zl];
+    float o[kZsPPT];
     if (e.x < 0) {  // this output plane maps outside the source: zeros
 #pragma unroll
-      for (int i = 0; i < kZsPPT; ++i)
-        if (ooff[i] >= 0) st_global_cs(out_tile + ooff[i], 0.0f);
-      continue;
-    }
+      for (int i = 0; i < kZsPPT; ++i) o[i] = 0.0f;
+    } else {
+      if (e.x > s_last) {  // CTA-uniform
+        fetch_plane();
+        s_last = e.x;
+      }
+      if (e.y > s_last) {
+        fetch_plane();
+        s_last = e.y;
+      }
+      if (ORDER == 0 || e.x == s_last) {  // single plane (nearest, or the +1 plane was clamped away)
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int s = h ? e.y : e.x;
-      if (s > s_last) {  // CTA-uniform: the next plane of the producer's sequence
-        const uint32_t stage = seq % kZsStages;
-        mbar_wait(&full_bar[stage], (seq / kZsStages) & 1);
-        const uint32_t base = stage0 + stage * g.stage_bytes;
+        for (int i = 0; i < kZsPPT; ++i) o[i] = p_last[i];
+      } else {
+        const float wz0 = __int_as_float(e.z), wz1 = __int_as_float(e.w);
 #pragma unroll
-        for (int i = 0; i < kZsPPT; ++i) {
-          const uint32_t a0 = base + off[i];
-          float v;
-          if (ORDER == 0) {
-            v = lds_elem<T>(a0);
-            if (SCRUB && sizeof(T) == 4) v = scrub_value(v);
-            v = __fmul_rn(v, w00[i]);  // w00 is 1 inside, 0 outside
-          } else {
-            const uint32_t a1 = a0 + pitch;
-            const float v00 = lds_elem<T>(a0);
-            const float v01 = lds_elem<T>(a0 + sizeof(T));
-            const float v10 = lds_elem<T>(a1);
-            const float v11 = lds_elem<T>(a1 + sizeof(T));
-            v = __fmaf_rn(w11[i], v11,
-                          __fmaf_rn(w10[i], v10, __fmaf_rn(w01[i], v01, __fmul_rn(w00[i], v00))));
-            if (SCRUB && sizeof(T) == 4 && !(fabsf(v) <= FLT_MAX)) {
-              // a NaN/inf tap was involved (possibly with zero weight): redo with the scrub
-              v = __fmaf_rn(w11[i], scrub_value(v11),
-                            __fmaf_rn(w10[i], scrub_value(v10),
-                                      __fmaf_rn(w01[i], scrub_value(v01),
-                                                __fmul_rn(w00[i], scrub_value(v00)))));
-            }
-          }
-          // un-scrubbed float sources may hold NaN at the dummy tap of an outside point
-          if (sizeof(T) == 4 && !SCRUB && !((inmask >> i) & 1u)) v = 0.0f;
-          p_prev[i] = p_last[i];
-          p_last[i] = v;
-        }
-        __syncwarp();
-        if ((tid & 31) == 0) mbar_arrive(&empty_bar[stage]);
-        s_last = s;
-        ++seq;
+        for (int i = 0; i < kZsPPT; ++i)
+          o[i] = __fmaf_rn(wz1, p_last[i], __fmul_rn(wz0, p_prev[i]));
       }
     }
-    if (ORDER == 0 || e.x == s_last) {  // single plane (nearest, or the +1 plane was clamped away)
+    if (full_tile) {
 #pragma unroll
-      for (int i = 0; i < kZsPPT; ++i)
-        if (ooff[i] >= 0) st_global_cs(out_tile + ooff[i], p_last[i]);
+      for (int i = 0; i < kZsPPT; ++i) st_global_cs(out_tile + ooff[i], o[i]);
     } else {
-      const float wz0 = __int_as_float(e.z), wz1 = __int_as_float(e.w);
 #pragma unroll
       for (int i = 0; i < kZsPPT; ++i)
-        if (ooff[i] >= 0)
-          st_global_cs(out_tile + ooff[i], __fmaf_rn(wz1, p_last[i], __fmul_rn(wz0, p_prev[i])));
+        if (ooff[i] >= 0) st_global_cs(out_tile + ooff[i], o[i]);
     }
   }
 }
@@ -296,7 +328,11 @@ static bool zsep_geometry(const AffineParams& p, ZsepGeom* g, size_t* smem_bytes
   const int bank_elems = 128 / static_cast<int>(sizeof(T));
   const int BX_banked = (BX + bank_elems - 1) / bank_elems * bank_elems;
   auto stage_of = [&](int bx) { return (BY * bx * static_cast<int>(sizeof(T)) + 127) / 128 * 128; };
-  if (BX_banked <= 256 && stage_of(BX_banked) * kZsStages <= 56 * 1024) BX = BX_banked;
+  static const bool use_banked = [] {
+    const char* e = getenv("B2_ZS_BANK");
+    return e ? atoi(e) != 0 : false;
+  }();
+  if (use_banked && BX_banked <= 256 && stage_of(BX_banked) * kZsStages <= 56 * 1024) BX = BX_banked;
   if (BY > 256 || BX > 256) return false;
   const int stage = stage_of(BX);
   if (stage * kZsStages > 96 * 1024) return false;
