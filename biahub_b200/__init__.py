@@ -28,11 +28,14 @@ from .register import (  # noqa: F401
     apply_affine_transform,
     convert_transform_to_ants,
     convert_transform_to_numpy,
+    find_lir,
+    find_overlapping_volume,
     get_3D_fliplr_matrix,
     get_3D_rescaling_matrix,
     get_3D_rotation_matrix,
     rescale_voxel_size,
 )
+from .pipeline import deskew_then_register  # noqa: F401
 from .stabilize import apply_stabilization_transform  # noqa: F401
 
 __version__ = "0.1.0"

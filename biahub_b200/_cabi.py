@@ -31,7 +31,7 @@ LIB_PATH = os.path.join(_PKG_DIR, "_lib", "libbiahub_b200.so")
 
 EXPORTS = (
     "b2_abi_version", "b2_last_error", "b2_device_count", "b2_check_device", "b2_deskew",
-    "b2_affine3d", "b2_overhang_fill_workspace", "b2_overhang_fill", "b2h_deskew",
+    "b2_affine3d", "b2_deskew_pitched", "b2_affine3d_pitched", "b2_overhang_fill_workspace", "b2_overhang_fill", "b2h_deskew",
     "b2h_affine3d", "b2h_release", "b2_launch_count",
 )
 
@@ -76,6 +76,11 @@ def lib() -> ctypes.CDLL:
         handle.b2_affine3d.argtypes = [_vp, _int, _i64, _i64, _i64, _vp, _i64, _i64, _i64,
                                        ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_i64),
                                        _int, _int, _int, _int, _vp]
+        handle.b2_deskew_pitched.argtypes = [_vp, _int, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _i64,
+                                             _i64, _int, _f32, _f32, _f32, _int, _vp]
+        handle.b2_affine3d_pitched.argtypes = [_vp, _int, _i64, _i64, _i64, _i64, _vp, _i64, _i64,
+                                               _i64, _i64, ctypes.POINTER(ctypes.c_double),
+                                               ctypes.POINTER(_i64), _int, _int, _int, _int, _vp]
         handle.b2_overhang_fill_workspace.argtypes = [_i64, _i64, _i64]
         handle.b2_overhang_fill_workspace.restype = ctypes.c_size_t
         handle.b2_overhang_fill.argtypes = [_vp, _i64, _i64, _i64, _int, _f32, _int, _vp,

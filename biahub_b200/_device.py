@@ -88,8 +88,32 @@ def host_source(arr):
     return arr, code
 
 
-def device_source(tensor):
-    """Return (contiguous CUDA tensor, B2 dtype code) for the b2_* calls."""
+def row_pitch(tensor):
+    """Row pitch (elements) of a (Z, Y, X) tensor whose rows are dense and whose planes are
+    Y*pitch apart (what ``padded_empty`` produces), else None."""
+    if tensor.ndim != 3:
+        return None
+    sz, sy, sx = tensor.stride()
+    Z, Y, X = tensor.shape
+    if sx == 1 and sy >= X and (sz == sy * Y or Z == 1):
+        return int(sy)
+    return None
+
+
+def padded_empty(shape, device, row_align=4):
+    """float32 CUDA tensor view of ``shape`` whose row pitch is rounded up to ``row_align``
+    elements (16-byte aligned rows → TMA-eligible source for a chained affine warp)."""
+    import torch
+
+    Z, Y, X = (int(v) for v in shape)
+    pitch = -(-X // row_align) * row_align
+    buf = torch.empty((Z, Y, pitch), dtype=torch.float32, device=device)
+    return buf[:, :, :X]
+
+
+def device_source(tensor, allow_pitched=False):
+    """Return (CUDA tensor, B2 dtype code) for the b2_* calls: contiguous, or — when
+    ``allow_pitched`` — a dense-row view with a row pitch (see ``row_pitch``)."""
     import torch
 
     if not tensor.is_cuda:
@@ -103,6 +127,8 @@ def device_source(tensor):
         if tensor.dtype != torch.float32:
             tensor = tensor.to(torch.float32)
         code = _cabi.DTYPE_F32
+    if allow_pitched and row_pitch(tensor) is not None:
+        return tensor, code
     return tensor.contiguous(), code
 
 

@@ -55,10 +55,12 @@ int sm_count(int* out) {
 // implemented in the kernel translation units
 int deskew_device(const void* src, int src_dtype, int64_t Zi, int64_t Yi, int64_t Xi, float* dst,
                   int64_t Zavg, int64_t Yo, int64_t Xo, int64_t Zo_full, int N, float px32,
-                  float pxct32, float off32, int path, cudaStream_t stream, const int* slab);
+                  float pxct32, float off32, int path, cudaStream_t stream, const int* slab,
+                  int64_t dst_row_pitch);
 int affine_device(const void* src, int src_dtype, int64_t sz, int64_t sy, int64_t sx, float* dst,
                   int64_t oz, int64_t oy, int64_t ox, const double* M12, const int64_t* crop_start,
-                  int order, int boundary, int scrub, int path, cudaStream_t stream);
+                  int order, int boundary, int scrub, int path, cudaStream_t stream,
+                  int64_t src_row_pitch, int64_t dst_row_pitch);
 size_t fill_workspace_bytes(int64_t z, int64_t y, int64_t x);
 int fill_device(float* vol, int64_t z, int64_t y, int64_t x, int use_mean, float fill_value,
                 int iterations, void* ws, size_t ws_bytes, cudaStream_t stream);
@@ -120,7 +122,18 @@ int b2_deskew(const void* src, int src_dtype, int64_t Zi, int64_t Yi, int64_t Xi
   if (rc) return rc;
   return b2::deskew_device(src, src_dtype, Zi, Yi, Xi, dst, Zavg, Yo, Xo, Zo_full,
                            average_n_slices, px32, pxct32, off32, path,
-                           static_cast<cudaStream_t>(stream), nullptr);
+                           static_cast<cudaStream_t>(stream), nullptr, 0);
+}
+
+int b2_deskew_pitched(const void* src, int src_dtype, int64_t Zi, int64_t Yi, int64_t Xi,
+                      float* dst, int64_t dst_row_pitch, int64_t Zavg, int64_t Yo, int64_t Xo,
+                      int64_t Zo_full, int average_n_slices, float px32, float pxct32, float off32,
+                      int path, void* stream) {
+  int rc = b2::require_device();
+  if (rc) return rc;
+  return b2::deskew_device(src, src_dtype, Zi, Yi, Xi, dst, Zavg, Yo, Xo, Zo_full,
+                           average_n_slices, px32, pxct32, off32, path,
+                           static_cast<cudaStream_t>(stream), nullptr, dst_row_pitch);
 }
 
 int b2_affine3d(const void* src, int src_dtype, int64_t sz, int64_t sy, int64_t sx, float* dst,
@@ -129,7 +142,18 @@ int b2_affine3d(const void* src, int src_dtype, int64_t sz, int64_t sy, int64_t 
   int rc = b2::require_device();
   if (rc) return rc;
   return b2::affine_device(src, src_dtype, sz, sy, sx, dst, oz, oy, ox, M12, crop_start, order,
-                           boundary, scrub_nonfinite, path, static_cast<cudaStream_t>(stream));
+                           boundary, scrub_nonfinite, path, static_cast<cudaStream_t>(stream), 0, 0);
+}
+
+int b2_affine3d_pitched(const void* src, int src_dtype, int64_t src_row_pitch, int64_t sz,
+                        int64_t sy, int64_t sx, float* dst, int64_t dst_row_pitch, int64_t oz,
+                        int64_t oy, int64_t ox, const double* M12, const int64_t* crop_start,
+                        int order, int boundary, int scrub_nonfinite, int path, void* stream) {
+  int rc = b2::require_device();
+  if (rc) return rc;
+  return b2::affine_device(src, src_dtype, sz, sy, sx, dst, oz, oy, ox, M12, crop_start, order,
+                           boundary, scrub_nonfinite, path, static_cast<cudaStream_t>(stream),
+                           src_row_pitch, dst_row_pitch);
 }
 
 size_t b2_overhang_fill_workspace(int64_t z, int64_t y, int64_t x) {

@@ -25,6 +25,7 @@ struct AffineParams {
   int order;          // 0 | 1
   int boundary;       // B2_BOUNDARY_*
   int scrub;          // scrub NaN/inf on load (float32 sources only)
+  int spitch, dpitch; // source / output row pitch in elements (planes are rows*pitch apart)
 };
 
 #ifdef __CUDACC__
@@ -87,7 +88,7 @@ __device__ __forceinline__ float lerp_w(float v0, float v1, float w) {
 template <typename T, int ORDER, int BOUNDARY, bool SCRUB>
 __device__ __forceinline__ float affine_sample_generic(const AffineParams& p, int z, int y, int x) {
   const T* __restrict__ src = static_cast<const T*>(p.src);
-  const int64_t sxy = static_cast<int64_t>(p.sy) * p.sx;
+  const int64_t sxy = static_cast<int64_t>(p.sy) * p.spitch;
   const double zf = static_cast<double>(z + p.cz);
   const double yf = static_cast<double>(y + p.cy);
   const double xf = static_cast<double>(x + p.cx);
@@ -103,10 +104,10 @@ __device__ __forceinline__ float affine_sample_generic(const AffineParams& p, in
   const AxisTap tx = resolve_axis<ORDER, BOUNDARY>(c[2], p.sx);
   if (!(tz.inside && ty.inside && tx.inside)) return 0.0f;
   const T* b0 = src + tz.i0 * sxy;
-  if (ORDER == 0) return load_tap<T, SCRUB>(b0 + static_cast<int64_t>(ty.i0) * p.sx + tx.i0);
+  if (ORDER == 0) return load_tap<T, SCRUB>(b0 + static_cast<int64_t>(ty.i0) * p.spitch + tx.i0);
   const T* b1 = src + tz.i1 * sxy;
-  const int64_t r0 = static_cast<int64_t>(ty.i0) * p.sx;
-  const int64_t r1 = static_cast<int64_t>(ty.i1) * p.sx;
+  const int64_t r0 = static_cast<int64_t>(ty.i0) * p.spitch;
+  const int64_t r1 = static_cast<int64_t>(ty.i1) * p.spitch;
   const float v000 = load_tap<T, SCRUB>(b0 + r0 + tx.i0);
   const float v001 = load_tap<T, SCRUB>(b0 + r0 + tx.i1);
   const float v010 = load_tap<T, SCRUB>(b0 + r1 + tx.i0);

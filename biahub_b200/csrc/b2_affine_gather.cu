@@ -15,7 +15,7 @@ __global__ void __launch_bounds__(256) affine_gather_kernel(const AffineParams p
     const int y = static_cast<int>(r % p.oy);
     const int z = static_cast<int>(r / p.oy);
     const float v = affine_sample_generic<T, ORDER, BOUNDARY, SCRUB>(p, z, y, x);
-    p.dst[idx] = v;
+    p.dst[r * p.dpitch + x] = v;
   }
 }
 
@@ -59,7 +59,8 @@ int affine_gather_launch(const AffineParams& p, int src_dtype, cudaStream_t stre
 // ---------------------------------------------------------------------------------------------
 int affine_device(const void* src, int src_dtype, int64_t sz, int64_t sy, int64_t sx, float* dst,
                   int64_t oz, int64_t oy, int64_t ox, const double* M12, const int64_t* crop_start,
-                  int order, int boundary, int scrub, int path, cudaStream_t stream) {
+                  int order, int boundary, int scrub, int path, cudaStream_t stream,
+                  int64_t src_row_pitch, int64_t dst_row_pitch) {
   if (!src || !dst || !M12) {
     set_error("affine3d: null pointer");
     return B2_ERR_INVALID;
@@ -100,6 +101,13 @@ int affine_device(const void* src, int src_dtype, int64_t sz, int64_t sy, int64_
   p.order = order;
   p.boundary = boundary;
   p.scrub = scrub ? 1 : 0;
+  if ((src_row_pitch != 0 && (src_row_pitch < sx || src_row_pitch > lim)) ||
+      (dst_row_pitch != 0 && (dst_row_pitch < ox || dst_row_pitch > lim))) {
+    set_error("affine3d: row pitch smaller than the row length");
+    return B2_ERR_INVALID;
+  }
+  p.spitch = src_row_pitch ? (int)src_row_pitch : (int)sx;
+  p.dpitch = dst_row_pitch ? (int)dst_row_pitch : (int)ox;
   if (oz == 0 || oy == 0 || ox == 0) return B2_OK;
 
   if (path != B2_PATH_GATHER) {

@@ -64,7 +64,7 @@ __device__ __noinline__ void zsep_tile_from_global(const AffineParams& p, int y0
     const int y = y0 + (i / kZsTX) % kZsTY;
     const int z = zb + i / (kZsTX * kZsTY);
     if (y < p.oy && x < p.ox)
-      p.dst[(static_cast<int64_t>(z) * p.oy + y) * p.ox + x] =
+      p.dst[(static_cast<int64_t>(z) * p.oy + y) * p.dpitch + x] =
           affine_sample_generic<T, ORDER, BOUNDARY, SCRUB>(p, z, y, x);
   }
 }
@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(kZsThreads, 3)
     const AxisTap ty = resolve_axis<ORDER, BOUNDARY>(coord_yx(yf, xf, p.m + 4), p.sy);
     const AxisTap tx = resolve_axis<ORDER, BOUNDARY>(coord_yx(yf, xf, p.m + 8), p.sx);
     const bool in = live && ty.inside && tx.inside;
-    ooff[i] = live ? yy * p.ox + lx : -1;
+    ooff[i] = live ? yy * p.dpitch + lx : -1;
     inmask |= in ? (1u << i) : 0u;
     off[i] = in ? static_cast<uint32_t>(ty.i0 - by0) * pitch +
                       static_cast<uint32_t>(tx.i0 - bx0) * static_cast<uint32_t>(sizeof(T))
@@ -206,9 +206,9 @@ __global__ void __launch_bounds__(kZsThreads, 3)
   for (int i = 0; i < kZsPPT; ++i) p_prev[i] = p_last[i] = 0.0f;
   int s_last = INT_MIN;
   uint32_t seq = 0;
-  const int64_t plane_out = static_cast<int64_t>(p.oy) * p.ox;
+  const int64_t plane_out = static_cast<int64_t>(p.oy) * p.dpitch;
   float* __restrict__ out_tile =
-      p.dst + static_cast<int64_t>(zb) * plane_out + static_cast<int64_t>(y0) * p.ox + x0;
+      p.dst + static_cast<int64_t>(zb) * plane_out + static_cast<int64_t>(y0) * p.dpitch + x0;
   const uint32_t full0 = smem_u32(&full_bar[0]);
   const uint32_t empty0 = smem_u32(&empty_bar[0]);
   const bool full_tile = (y0 + kZsTY <= p.oy) && (x0 + kZsTX <= p.ox);  // CTA-uniform
@@ -315,7 +315,7 @@ static bool zsep_geometry(const AffineParams& p, ZsepGeom* g, size_t* smem_bytes
   if (m[1] != 0.0 || m[2] != 0.0 || m[4] != 0.0 || m[8] != 0.0) return false;
   if (!(m[0] > 0.0)) return false;
   if (reinterpret_cast<uintptr_t>(p.src) % 16 != 0) return false;
-  if ((static_cast<int64_t>(p.sx) * sizeof(T)) % 16 != 0) return false;
+  if ((static_cast<int64_t>(p.spitch) * sizeof(T)) % 16 != 0) return false;
   const double ey = fabs(m[5]) * (kZsTY - 1) + fabs(m[6]) * (kZsTX - 1);
   const double ex = fabs(m[9]) * (kZsTY - 1) + fabs(m[10]) * (kZsTX - 1);
   if (!(ey < 240.0) || !(ex < 240.0)) return false;
@@ -336,7 +336,7 @@ static bool zsep_geometry(const AffineParams& p, ZsepGeom* g, size_t* smem_bytes
   if (BY > 256 || BX > 256) return false;
   const int stage = stage_of(BX);
   if (stage * kZsStages > 96 * 1024) return false;
-  if (static_cast<int64_t>(kZsTY) * p.ox >= (1LL << 31)) return false;
+  if (static_cast<int64_t>(kZsTY) * p.dpitch >= (1LL << 31)) return false;
   g->BY = BY;
   g->BX = BX;
   g->stage_bytes = stage;
@@ -354,8 +354,8 @@ static int launch_zsep(const AffineParams& p, ZsepGeom g, size_t smem_bytes, cud
   CUtensorMap map;
   const cuuint64_t gdim[3] = {static_cast<cuuint64_t>(p.sx), static_cast<cuuint64_t>(p.sy),
                               static_cast<cuuint64_t>(p.sz)};
-  const cuuint64_t gstride[2] = {static_cast<cuuint64_t>(p.sx) * sizeof(T),
-                                 static_cast<cuuint64_t>(p.sx) * p.sy * sizeof(T)};
+  const cuuint64_t gstride[2] = {static_cast<cuuint64_t>(p.spitch) * sizeof(T),
+                                 static_cast<cuuint64_t>(p.spitch) * p.sy * sizeof(T)};
   const cuuint32_t box[3] = {static_cast<cuuint32_t>(g.BX), static_cast<cuuint32_t>(g.BY), 1u};
   const cuuint32_t estride[3] = {1, 1, 1};
   const CUtensorMapDataType dt =

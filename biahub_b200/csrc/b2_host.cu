@@ -28,10 +28,12 @@ namespace b2 {
 
 int deskew_device(const void* src, int src_dtype, int64_t Zi, int64_t Yi, int64_t Xi, float* dst,
                   int64_t Zavg, int64_t Yo, int64_t Xo, int64_t Zo_full, int N, float px32,
-                  float pxct32, float off32, int path, cudaStream_t stream, const int* slab);
+                  float pxct32, float off32, int path, cudaStream_t stream, const int* slab,
+                  int64_t dst_row_pitch);
 int affine_device(const void* src, int src_dtype, int64_t sz, int64_t sy, int64_t sx, float* dst,
                   int64_t oz, int64_t oy, int64_t ox, const double* M12, const int64_t* crop_start,
-                  int order, int boundary, int scrub, int path, cudaStream_t stream);
+                  int order, int boundary, int scrub, int path, cudaStream_t stream,
+                  int64_t src_row_pitch, int64_t dst_row_pitch);
 
 namespace {
 
@@ -378,7 +380,7 @@ int host_deskew(const void* h_src, int src_dtype, int64_t Zi, int64_t Yi, int64_
     s.launch = [=](cudaStream_t st) {
       const int slab[4] = {0, static_cast<int>(Yi), static_cast<int>(a0), static_cast<int>(cnt)};
       return deskew_device(d_src, src_dtype, Zi, Yi, Xi, d_dst + a0 * Yo * Xo, Zavg, Yo, Xo,
-                           Zo_full, N, px32, pxct32, off32, B2_PATH_AUTO, st, slab);
+                           Zo_full, N, px32, pxct32, off32, B2_PATH_AUTO, st, slab, 0);
     };
     slabs.push_back(std::move(s));
   }
@@ -469,7 +471,7 @@ int host_affine(const void* h_src, int src_dtype, int64_t sz, int64_t sy, int64_
     s.launch = [=](cudaStream_t st) {
       const int64_t crop[3] = {c0[0] + z0, c0[1], c0[2]};
       return affine_device(d_src, src_dtype, sz, sy, sx, d_dst + z0 * oy * ox, cnt, oy, ox,
-                           M.data(), crop, order, boundary, scrub, B2_PATH_AUTO, st);
+                           M.data(), crop, order, boundary, scrub, B2_PATH_AUTO, st, 0, 0);
     };
     slabs.push_back(std::move(s));
   }

@@ -20,7 +20,8 @@ from typing import Literal
 import numpy as np
 
 from . import _cabi
-from ._device import check_out, device_source, host_source, is_torch_tensor, resolve_device
+from ._device import (check_out, device_source, host_source, is_torch_tensor, padded_empty,
+                      resolve_device, row_pitch)
 
 __all__ = [
     "_average_n_slices", "_get_averaged_shape", "_get_transform_matrix", "get_deskewed_data_shape",
@@ -140,11 +141,14 @@ def fast_deskew_zyx(
     average_n_slices: int = 1,
     overhang_fill: Literal["mean"] | float = 0,
     *,
+    row_align: int = 1,
     _path: int = _cabi.PATH_AUTO,
 ):
     """Deskew a (Z_scan, Y_tilt, X_coverslip) CUDA tensor → float32 CUDA tensor
     (ceil(Y/N), X, X_out).  Signature and semantics of reference deskew.py:456-542; float32 and
-    uint16 tensors are consumed as they are, other dtypes are cast to float32 first."""
+    uint16 tensors are consumed as they are, other dtypes are cast to float32 first.
+    ``row_align`` (extension): round the output row pitch up to that many elements and return a
+    view — ``row_align=4`` makes the result a TMA-eligible source for a chained ``affine_warp``."""
     import torch
 
     if not is_torch_tensor(raw_data):
@@ -156,12 +160,15 @@ def fast_deskew_zyx(
     do_fill, use_mean, value = _fill_args(keep_overhang, overhang_fill)
     lib = _cabi.lib()
     with torch.cuda.device(src.device):
-        out = torch.empty((s["Zavg"], s["Yo"], s["Xo"]), dtype=torch.float32, device=src.device)
+        out = padded_empty((s["Zavg"], s["Yo"], s["Xo"]), src.device, max(1, int(row_align)))
         stream = torch.cuda.current_stream().cuda_stream
-        _cabi.check(lib.b2_deskew(
-            src.data_ptr(), code, s["Zi"], s["Yi"], s["Xi"], out.data_ptr(), s["Zavg"], s["Yo"],
-            s["Xo"], s["Zo"], s["N"], s["px32"], s["pxct32"], s["off32"], int(_path), stream))
+        _cabi.check(lib.b2_deskew_pitched(
+            src.data_ptr(), code, s["Zi"], s["Yi"], s["Xi"], out.data_ptr(), row_pitch(out),
+            s["Zavg"], s["Yo"], s["Xo"], s["Zo"], s["N"], s["px32"], s["pxct32"], s["off32"],
+            int(_path), stream))
         if do_fill:
+            if not out.is_contiguous():
+                raise NotImplementedError("overhang_fill with a padded row pitch")
             nbytes = lib.b2_overhang_fill_workspace(s["Zavg"], s["Yo"], s["Xo"])
             ws = torch.empty(nbytes, dtype=torch.uint8, device=src.device)
             _cabi.check(lib.b2_overhang_fill(

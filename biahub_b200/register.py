@@ -21,12 +21,14 @@ import ctypes
 import numpy as np
 
 from . import _cabi
-from ._device import check_out, device_source, host_source, is_torch_tensor, resolve_device
+from ._device import (check_out, device_source, host_source, is_torch_tensor, padded_empty,
+                      resolve_device, row_pitch)
 
 __all__ = [
     "get_3D_rescaling_matrix", "get_3D_rotation_matrix", "get_3D_fliplr_matrix",
     "convert_transform_to_ants", "convert_transform_to_numpy", "apply_affine_transform",
-    "affine_warp", "rescale_voxel_size", "ItkAffineParameters",
+    "affine_warp", "rescale_voxel_size", "ItkAffineParameters", "largest_interior_rectangle",
+    "find_lir", "find_overlapping_volume",
 ]
 
 _INTERPOLATION_ORDER = {"linear": 1, "nearestneighbor": 0}
@@ -165,7 +167,7 @@ def _crop_box(output_shape_zyx, crop_output_slicing):
 
 def affine_warp(data, matrix, output_shape_zyx, order: int = 1, boundary: str = "itk",
                 crop_output_slicing=None, scrub_nonfinite: bool = True, device=None,
-                out=None, _path: int = _cabi.PATH_AUTO):
+                out=None, row_align: int = 1, _path: int = _cabi.PATH_AUTO):
     """Pull-warp a (Z, Y, X) volume: numpy in → numpy float32 out (host pipeline), or CUDA
     tensor in → CUDA float32 tensor out (kernel only, on the current stream).
 
@@ -186,13 +188,14 @@ def affine_warp(data, matrix, output_shape_zyx, order: int = 1, boundary: str = 
 
         if data.ndim != 3:
             raise ValueError("expected a (Z, Y, X) tensor")
-        src, code = device_source(data)
+        src, code = device_source(data, allow_pitched=True)
         with torch.cuda.device(src.device):
-            out = torch.empty(sizes, dtype=torch.float32, device=src.device)
+            out = padded_empty(sizes, src.device, max(1, int(row_align)))
             if out.numel():
-                _cabi.check(lib.b2_affine3d(
-                    src.data_ptr(), code, *src.shape, out.data_ptr(), *sizes, m12, crop, int(order),
-                    bcode, int(bool(scrub_nonfinite)), int(_path),
+                _cabi.check(lib.b2_affine3d_pitched(
+                    src.data_ptr(), code, row_pitch(src), *src.shape, out.data_ptr(),
+                    row_pitch(out), *sizes, m12, crop, int(order), bcode,
+                    int(bool(scrub_nonfinite)), int(_path),
                     torch.cuda.current_stream().cuda_stream))
         return out
 
@@ -250,3 +253,75 @@ def apply_affine_transform(
     if ndim != 3:
         raise ValueError("zyx_data must be (Z, Y, X) or (C, Z, Y, X)")
     return affine_warp(zyx_data, matrix, output_shape_zyx, order, boundary, crop_output_slicing)
+
+
+# ------------------------------------------------------------------------------------------
+# output-shape logic of `biahub register` when keep_overhang=False (reference register.py:284-394)
+# ------------------------------------------------------------------------------------------
+def largest_interior_rectangle(mask2d) -> tuple:
+    """Largest axis-aligned all-True rectangle of a 2-D boolean mask → ``(x, y, width, height)``
+    (the return convention of the third-party ``largestinteriorrectangle.lir`` the reference
+    calls at register.py:289-309).  Histogram/stack sweep, O(H*W); ties keep the first
+    rectangle found scanning rows top to bottom."""
+    m = np.asarray(mask2d, dtype=bool)
+    if m.ndim != 2:
+        raise ValueError("mask must be 2-D")
+    H, W = m.shape
+    heights = np.zeros(W + 1, dtype=np.int64)  # sentinel column of height 0
+    best = (0, 0, 0, 0)
+    best_area = 0
+    for row in range(H):
+        heights[:W] = np.where(m[row], heights[:W] + 1, 0)
+        stack = []  # (start column, height)
+        for col in range(W + 1):
+            h = int(heights[col])
+            start = col
+            while stack and stack[-1][1] >= h:
+                s0, h0 = stack.pop()
+                area = h0 * (col - s0)
+                if area > best_area:
+                    best_area = area
+                    best = (s0, row - h0 + 1, col - s0, h0)
+                start = s0
+            if h > 0:
+                stack.append((start, h))
+    return best
+
+
+def find_lir(registered_zyx: np.ndarray, plot: bool = False) -> tuple:
+    """ZYX slices of a large interior cuboid of a boolean volume, with the reference's recipe
+    (register.py:284-342): largest interior rectangle in YX at Z//2, then the Z extent common to
+    the ZY / ZX rectangles probed at three x and three y positions."""
+    vol = np.asarray(registered_zyx, dtype=bool)
+    x, y, width, height = largest_interior_rectangle(vol[vol.shape[0] // 2])
+    x_start, x_stop = x, x + width
+    y_start, y_stop = y, y + height
+    x_slice, y_slice = slice(x_start, x_stop), slice(y_start, y_stop)
+    z_ranges = []
+    for _x in (x_start, x_start + (x_stop - x_start) // 2, x_stop - 1):
+        _, z, _, depth = largest_interior_rectangle(vol[:, y_slice, _x])
+        z_ranges.append((z, z + depth))
+    for _y in (y_start, y_start + (y_stop - y_start) // 2, y_stop - 1):
+        _, z, _, depth = largest_interior_rectangle(vol[:, _y, x_slice])
+        z_ranges.append((z, z + depth))
+    z_ranges = np.asarray(z_ranges)
+    z_slice = slice(int(z_ranges[:, 0].max()), int(z_ranges[:, 1].min()))
+    return (z_slice, y_slice, x_slice)
+
+
+def find_overlapping_volume(input_zyx_shape, target_zyx_shape, transformation_matrix,
+                            method: str = "LIR", plot: bool = False, device=None) -> tuple:
+    """ZYX slices of the overlap of a warped source with the target grid (reference
+    register.py:345-394): warp a volume of ones onto the target grid, ``mask = warped > 0``, then
+    ``find_lir``.  The ones volume is created and warped on the GPU (uint16 ones, linear
+    interpolation, ITK boundary rule); only the boolean mask comes back to the host."""
+    import torch
+
+    if method != "LIR":
+        raise ValueError(f"Unknown method {method}")
+    dev = torch.device("cuda", resolve_device(device))
+    ones = torch.ones(tuple(int(v) for v in input_zyx_shape), dtype=torch.float32, device=dev)
+    warped = affine_warp(ones, transformation_matrix, tuple(int(v) for v in target_zyx_shape),
+                         order=1, boundary="itk", scrub_nonfinite=False)
+    mask = (warped > 0).cpu().numpy()
+    return find_lir(mask, plot=plot)

@@ -79,6 +79,14 @@ B2_API int b2_deskew(const void* src, int src_dtype, int64_t Zi, int64_t Yi, int
               int average_n_slices, float px32, float pxct32, float off32,
               int path, void* stream);
 
+/* Same as b2_deskew with an explicit output row pitch (elements, >= Xo; planes are Yo*pitch
+ * apart).  A pitch that is a multiple of 4 keeps the rows 16-byte aligned so that a following
+ * b2_affine3d_pitched can stage the deskewed volume with TMA (chained deskew -> register). */
+B2_API int b2_deskew_pitched(const void* src, int src_dtype, int64_t Zi, int64_t Yi, int64_t Xi,
+                      float* dst, int64_t dst_row_pitch, int64_t Zavg, int64_t Yo, int64_t Xo,
+                      int64_t Zo_full, int average_n_slices, float px32, float pxct32, float off32,
+                      int path, void* stream);
+
 /*
  * Affine pull warp, order 0 (nearest) or 1 (trilinear), with NaN/inf scrub on load.
  * Replaces the arithmetic of reference `apply_affine_transform` (biahub/register.py:202-281:
@@ -95,6 +103,12 @@ B2_API int b2_affine3d(const void* src, int src_dtype, int64_t sz, int64_t sy, i
                 float* dst, int64_t oz, int64_t oy, int64_t ox,
                 const double* M12, const int64_t* crop_start,
                 int order, int boundary, int scrub_nonfinite, int path, void* stream);
+
+/* Same as b2_affine3d with explicit source / output row pitches in elements (0 = dense). */
+B2_API int b2_affine3d_pitched(const void* src, int src_dtype, int64_t src_row_pitch, int64_t sz,
+                        int64_t sy, int64_t sx, float* dst, int64_t dst_row_pitch, int64_t oz,
+                        int64_t oy, int64_t ox, const double* M12, const int64_t* crop_start,
+                        int order, int boundary, int scrub_nonfinite, int path, void* stream);
 
 /*
  * Overhang fill (reference `_fill_overhang_torch`, biahub/deskew.py:339-368): mask = (vol == 0)

@@ -212,3 +212,56 @@ def test_full_size_spot_check_c3_plane_count():
     got0 = affine_warp(_to_cuda(vol), M, shape, order=0, boundary="constant").cpu().numpy()
     want0 = ao.affine_oracle_points(vol, M, pts, 0, "constant")
     assert np.array_equal(got0[pts[:, 0], pts[:, 1], pts[:, 2]], want0)
+
+
+def test_pitched_chain_deskew_then_register():
+    """Chained deskew -> register keeps the intermediate on the device with a padded row pitch
+    (TMA-eligible) and must equal the two separate reference-facing calls bit for bit."""
+    import torch
+
+    import biahub_b200 as b2
+    from biahub_b200 import _cabi
+    from biahub_b200._device import row_pitch
+
+    rng = np.random.default_rng(12)
+    raw = rng.integers(0, 65536, size=(160, 24, 128), dtype=np.uint16)
+    kw = dict(ls_angle_deg=30.0, px_to_scan_ratio=0.386, keep_overhang=False, average_n_slices=3)
+    mid = b2._fast_deskew_czyx(raw[None], **kw)[0]            # (8, 128, 389): 389 % 4 != 0
+    assert mid.shape[2] % 4 != 0
+    M = ao.register_matrix_c3(mid.shape)
+    # dense odd-width rows go through the gather kernel (nested lerps), the padded chain through
+    # the TMA kernel (4-weight form): order 1 agrees to rounding, order 0 bit for bit
+    want = b2.apply_affine_transform(mid, M, mid.shape)
+    got = b2.deskew_then_register(raw, M, mid.shape, **kw)
+    assert np.abs(got - want).max() <= 2e-6 * 65535.0
+    want0 = b2.apply_affine_transform(mid, M, mid.shape, interpolation="nearestneighbor")
+    got0 = b2.deskew_then_register(raw, M, mid.shape, interpolation="nearestneighbor", **kw)
+    assert np.array_equal(got0, want0)
+    oracle = ao.affine_oracle_numpy(mid, M, mid.shape, 1, "itk")
+    assert np.abs(got - oracle).max() <= 1e-4 * 65535.0
+    # the padded intermediate is a strided view and takes the TMA path
+    t = torch.from_numpy(raw.view(np.int16)).cuda().view(torch.uint16)
+    padded = b2.fast_deskew_zyx(t, 30.0, 0.386, False, 3, row_align=4)
+    assert not padded.is_contiguous() and row_pitch(padded) % 4 == 0
+    assert np.array_equal(padded.cpu().numpy(), mid)
+    a = b2.affine_warp(padded, M, mid.shape, _path=_cabi.PATH_TMA)
+    assert np.array_equal(a.cpu().numpy(), got)
+    with pytest.raises(_cabi.B2Unsupported):                  # dense odd-width rows are not TMA-able
+        b2.affine_warp(torch.from_numpy(mid).cuda(), M, mid.shape, _path=_cabi.PATH_TMA)
+
+
+def test_find_overlapping_volume():
+    """register's keep_overhang=False crop (reference register.py:345-394): warp ones on the GPU,
+    largest interior rectangle on the host."""
+    import biahub_b200 as b2
+
+    M = np.eye(4)
+    M[:3, 3] = (-3, 1, 4)                      # reference tests/test_affine.py:43-59 geometry
+    z, y, x = b2.find_overlapping_volume((10, 10, 10), (10, 10, 10), M)
+    assert (z, y, x) == (slice(3, 10), slice(0, 9), slice(0, 6))
+    shape = (12, 96, 128)
+    M2 = ao.register_matrix_c3(shape)
+    z, y, x = b2.find_overlapping_volume(shape, shape, M2)
+    mask = ao.affine_oracle_numpy(np.ones(shape, np.float32), M2, shape, 1, "itk") > 0
+    assert mask[z, y, x].all()                  # the crop lies inside the warped support
+    assert (z.stop - z.start) * (y.stop - y.start) * (x.stop - x.start) > 0.5 * mask.sum()

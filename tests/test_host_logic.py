@@ -154,3 +154,30 @@ def test_device_resolution(monkeypatch):
     assert _device.resolve_device(1) == 1
     with pytest.raises(ValueError):
         _device.resolve_device("tpu")
+
+
+def test_find_lir_known_answer():
+    # reference tests/test_cli/test_register_cli.py:75-86
+    data = np.zeros((10, 10, 10))
+    data[2:8, 0:9, 3:10] = 1
+    z_slice, y_slice, x_slice = b2.find_lir(data)
+    assert (z_slice, y_slice, x_slice) == (slice(2, 8), slice(0, 9), slice(3, 10))
+
+
+def test_largest_interior_rectangle_bruteforce():
+    from biahub_b200.register import largest_interior_rectangle
+
+    rng = np.random.default_rng(0)
+    for _ in range(30):
+        m = rng.random((7, 9)) > 0.3
+        x, y, w, h = largest_interior_rectangle(m)
+        assert w * h == 0 or m[y:y + h, x:x + w].all()
+        best = 0
+        for y0 in range(7):
+            for y1 in range(y0 + 1, 8):
+                for x0 in range(9):
+                    for x1 in range(x0 + 1, 10):
+                        if m[y0:y1, x0:x1].all():
+                            best = max(best, (y1 - y0) * (x1 - x0))
+        assert w * h == best
+    assert largest_interior_rectangle(np.zeros((3, 3), bool)) == (0, 0, 0, 0)
