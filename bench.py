@@ -54,6 +54,11 @@ WORKLOADS = {
     "register_c3": dict(kind="register", shape=(120, 2048, 2048), dtype="float32", units=8,
                         e2e_units=2,
                         desc="C3 register float32 (Z=120,Y=2048,X=2048) rot 7.3deg scale 1.07 shift (0.4,3.25,-11.5) order 1"),
+    # C3 geometry with a NON z-separable matrix (small 3-D rotation about Y and X on top of C3):
+    # exercises the generic path
+    "register_generic": dict(kind="register", shape=(120, 2048, 2048), dtype="float32", units=8,
+                             e2e_units=2, generic=True,
+                             desc="C3 shape float32 (120,2048,2048), generic 3-D affine (C3 matrix + 0.5/0.3 deg out-of-plane rotations), order 1"),
     # configs[3]
     "stabilize_c4": dict(kind="stabilize", shape=(64, 2048, 2048), dtype="float32", units=16,
                          e2e_units=4,
@@ -157,6 +162,19 @@ def register_matrix_c3(shape, angle_deg=7.3, scale_yx=1.07, shift_zyx=(0.4, 3.25
             @ b2.get_3D_rescaling_matrix(shape, (1.0, scale_yx, scale_yx)))
 
 
+def out_of_plane_rotation(shape, deg_about_y, deg_about_x):
+    """Small rotations that mix Z with X and Z with Y about the volume centre."""
+    c = (np.array(shape) - 1) / 2.0
+    a, b = np.radians(deg_about_y), np.radians(deg_about_x)
+    Ry = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]])
+    Rx = np.array([[np.cos(b), -np.sin(b), 0], [np.sin(b), np.cos(b), 0], [0, 0, 1]])
+    R = Ry @ Rx
+    M = np.eye(4)
+    M[:3, :3] = R
+    M[:3, 3] = c - R @ c
+    return M
+
+
 def unit_geometry(w):
     """(out_shape, algorithmic bytes per unit, output voxels per unit)."""
     import biahub_b200 as b2
@@ -212,7 +230,10 @@ def run_b200(args, w, rank, world, local_rank):
     if w["kind"] == "chain":
         mats = [register_matrix_c3(out_shape)] * units
     elif w["kind"] == "register":
-        mats = [register_matrix_c3(w["shape"])] * units
+        M = register_matrix_c3(w["shape"])
+        if w.get("generic"):
+            M = M @ out_of_plane_rotation(w["shape"], 0.5, 0.3)
+        mats = [M] * units
     elif w["kind"] == "stabilize":
         mats = stabilize_matrices(units)
     outs = [None] * units
@@ -343,7 +364,7 @@ def run_b200(args, w, rank, world, local_rank):
                 "gpu_launches": int(launches_e2e), "checksum": check},
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                      "frac": round(achieved / peak, 4), "traffic": None,
-                     "kernel": {"deskew": "deskew_tma_kernel", "chain": "deskew_tma_kernel + affine_zsep_kernel (bytes and time of both)"}.get(w["kind"], "affine_zsep_kernel"),
+                     "kernel": {"deskew": "deskew_tma_kernel", "chain": "deskew_tma_kernel + affine_zsep_kernel (bytes and time of both)"}.get(w["kind"], "affine_gather_kernel" if w.get("generic") else "affine_zsep_kernel"),
                      "algorithmic_bytes_per_launch": int(bytes_unit),
                      "launch_ms": round(launch_ms, 4), "peak_source": peak_src},
     }

@@ -85,20 +85,26 @@ __device__ __forceinline__ float lerp_w(float v0, float v1, float w) {
 }
 
 // One output voxel of the generic warp: float64 coordinates in the oracle's op order, taps via LDG.
-template <typename T, int ORDER, int BOUNDARY, bool SCRUB>
-__device__ __forceinline__ float affine_sample_generic(const AffineParams& p, int z, int y, int x) {
-  const T* __restrict__ src = static_cast<const T*>(p.src);
-  const int64_t sxy = static_cast<int64_t>(p.sy) * p.spitch;
+// (t_d + z*m_d0) + y*m_d1 for the three axes: the part of the coordinate shared by a whole row
+__device__ __forceinline__ void affine_row_part(const AffineParams& p, int z, int y, double (&rp)[3]) {
   const double zf = static_cast<double>(z + p.cz);
   const double yf = static_cast<double>(y + p.cy);
-  const double xf = static_cast<double>(x + p.cx);
-  double c[3];
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
     const double* m = p.m + 4 * d;
-    c[d] = __dadd_rn(
-        __dadd_rn(__dadd_rn(m[3], __dmul_rn(zf, m[0])), __dmul_rn(yf, m[1])), __dmul_rn(xf, m[2]));
+    rp[d] = __dadd_rn(__dadd_rn(m[3], __dmul_rn(zf, m[0])), __dmul_rn(yf, m[1]));
   }
+}
+
+template <typename T, int ORDER, int BOUNDARY, bool SCRUB>
+__device__ __forceinline__ float affine_sample_row(const AffineParams& p, const double (&rp)[3],
+                                                   int x) {
+  const T* __restrict__ src = static_cast<const T*>(p.src);
+  const int64_t sxy = static_cast<int64_t>(p.sy) * p.spitch;
+  const double xf = static_cast<double>(x + p.cx);
+  double c[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) c[d] = __dadd_rn(rp[d], __dmul_rn(xf, p.m[4 * d + 2]));
   const AxisTap tz = resolve_axis<ORDER, BOUNDARY>(c[0], p.sz);
   const AxisTap ty = resolve_axis<ORDER, BOUNDARY>(c[1], p.sy);
   const AxisTap tx = resolve_axis<ORDER, BOUNDARY>(c[2], p.sx);
@@ -121,10 +127,18 @@ __device__ __forceinline__ float affine_sample_generic(const AffineParams& p, in
   return lerp_w(p0, p1, tz.w);
 }
 
+template <typename T, int ORDER, int BOUNDARY, bool SCRUB>
+__device__ __forceinline__ float affine_sample_generic(const AffineParams& p, int z, int y, int x) {
+  double rp[3];
+  affine_row_part(p, z, y, rp);
+  return affine_sample_row<T, ORDER, BOUNDARY, SCRUB>(p, rp, x);
+}
+
 #endif  // __CUDACC__
 
 int affine_gather_launch(const AffineParams& p, int src_dtype, cudaStream_t stream);
 // returns B2_ERR_UNSUPPORTED (without setting an error) when the matrix/shape is not eligible
 int affine_zsep_launch(const AffineParams& p, int src_dtype, cudaStream_t stream, bool* eligible);
+int affine_brick_launch(const AffineParams& p, int src_dtype, cudaStream_t stream, bool* eligible);
 
 }  // namespace b2

@@ -1,0 +1,357 @@
+// TMA-staged affine pull warp for GENERIC 3x4 matrices (out-of-plane rotations, shears, flips):
+// the case `affine_zsep_kernel` cannot take.  One CTA = one output tile (TZ x TY x TX); the
+// tile's back-projected bounding box is a 3-D brick of the source that is staged in shared
+// memory with ONE 3-D TMA box load (out-of-bounds zero fill, origin rounded down to 16 bytes).
+// Tiles are rasterised z-fastest so that tiles sharing z-halo planes run concurrently and the
+// halos are served from L2.
+//
+// Coordinates: each thread owns one (y, x) column of the tile and walks TZ output planes.  Its
+// first coordinate is evaluated in float64 in the oracle's op order and expressed relative to the
+// brick origin; along z it advances by fp32 increments (|error| ~1e-5 voxel, well inside the
+// 1e-4-of-range tolerance).  Any voxel whose coordinate comes within kEdge of a decision edge
+// (volume border, ITK half-voxel band, the k+0.5 rounding point of nearest-neighbour) is
+// re-evaluated exactly in float64 through `resolve_axis`, so inside/outside and nearest-neighbour
+// index decisions are identical to the float64 oracle (order 0 stays bit-exact).
+#include "b2_affine.cuh"
+
+namespace b2 {
+
+constexpr int kBrTZ = 8;
+constexpr int kBrTY = 16;
+constexpr int kBrTX = 32;
+constexpr int kBrThreads = 256;
+constexpr int kBrCols = (kBrTY * kBrTX) / kBrThreads;  // (y, x) columns per thread
+constexpr int kBrRowStep = kBrThreads / kBrTX;          // y distance between a thread's columns
+constexpr float kEdge = 2.0e-3f;
+constexpr float kMagic = 12582912.0f;  // 1.5 * 2^23: (v + kMagic) - kMagic rounds v to nearest
+
+struct BrickGeom {
+  int BZ, BY, BX;  // brick extent (elements)
+  int bytes;       // BZ*BY*BX*sizeof(T)
+  // hull of a full tile relative to its origin voxel: sum of the negative / positive parts of
+  // m_dj * (T_j - 1) per source axis d (host, float64)
+  double neg[3], pos[3];
+  float mcol[9];   // float32 copy of the 3x3 linear part (row-major) for the fp32 increments
+};
+
+template <typename T>
+__device__ __forceinline__ float brick_elem(uint32_t addr);
+template <>
+__device__ __forceinline__ float brick_elem<float>(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+template <>
+__device__ __forceinline__ float brick_elem<uint16_t>(uint32_t addr) {
+  unsigned short v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+  return static_cast<float>(v);
+}
+
+__device__ __forceinline__ double coord_full(const double* m, double zf, double yf, double xf) {
+  return __dadd_rn(__dadd_rn(__dadd_rn(m[3], __dmul_rn(zf, m[0])), __dmul_rn(yf, m[1])),
+                   __dmul_rn(xf, m[2]));
+}
+
+// exact (float64) evaluation of one voxel with taps read from the brick
+template <typename T, int ORDER, int BOUNDARY, bool SCRUB>
+__device__ __noinline__ float brick_sample_exact(const AffineParams& p, uint32_t brick, int bz0,
+                                                 int by0, int bx0, int BY, int BX, int z, int y,
+                                                 int x) {
+  const double zf = static_cast<double>(z + p.cz), yf = static_cast<double>(y + p.cy),
+               xf = static_cast<double>(x + p.cx);
+  const AxisTap tz = resolve_axis<ORDER, BOUNDARY>(coord_full(p.m, zf, yf, xf), p.sz);
+  const AxisTap ty = resolve_axis<ORDER, BOUNDARY>(coord_full(p.m + 4, zf, yf, xf), p.sy);
+  const AxisTap tx = resolve_axis<ORDER, BOUNDARY>(coord_full(p.m + 8, zf, yf, xf), p.sx);
+  if (!(tz.inside && ty.inside && tx.inside)) return 0.0f;
+  auto tap = [&](int iz, int iy, int ix) {
+    const uint32_t off = static_cast<uint32_t>(((iz - bz0) * BY + (iy - by0)) * BX + (ix - bx0));
+    float v = brick_elem<T>(brick + off * static_cast<uint32_t>(sizeof(T)));
+    if (SCRUB && sizeof(T) == 4) v = scrub_value(v);
+    return v;
+  };
+  if (ORDER == 0) return tap(tz.i0, ty.i0, tx.i0);
+  const float p0 = lerp_w(lerp_w(tap(tz.i0, ty.i0, tx.i0), tap(tz.i0, ty.i0, tx.i1), tx.w),
+                          lerp_w(tap(tz.i0, ty.i1, tx.i0), tap(tz.i0, ty.i1, tx.i1), tx.w), ty.w);
+  const float p1 = lerp_w(lerp_w(tap(tz.i1, ty.i0, tx.i0), tap(tz.i1, ty.i0, tx.i1), tx.w),
+                          lerp_w(tap(tz.i1, ty.i1, tx.i0), tap(tz.i1, ty.i1, tx.i1), tx.w), ty.w);
+  return lerp_w(p0, p1, tz.w);
+}
+
+template <typename T, int ORDER, int BOUNDARY, bool SCRUB>
+__global__ void __launch_bounds__(kBrThreads, 3)
+    affine_brick_kernel(const __grid_constant__ CUtensorMap src_map,
+                        const __grid_constant__ AffineParams p,
+                        const __grid_constant__ BrickGeom g, const int tiles_z, const int tiles_x) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t bar;
+  constexpr int kVec = 16 / static_cast<int>(sizeof(T));
+  const uint32_t brick = (smem_u32(smem_raw) + 127u) & ~127u;
+
+  // z-fastest rasterisation: consecutive CTAs share z-halo planes
+  const int tz_i = blockIdx.x % tiles_z;
+  const int tx_i = (blockIdx.x / tiles_z) % tiles_x;
+  const int ty_i = blockIdx.x / (tiles_z * tiles_x);
+  const int z0 = tz_i * kBrTZ, y0 = ty_i * kBrTY, x0 = tx_i * kBrTX;
+  const int nz = min(kBrTZ, p.oz - z0);
+
+  // ---- brick origin: exact float64 coordinate of the tile origin + the host-computed hull of a
+  //      full tile (CTA-uniform; the 1e-6 guards absorb the rounding of the hull sums; the host
+  //      guarantees |coordinate| < 1e9 over the whole output so the int conversions are defined)
+  int b0[3], bhi[3];
+  float c0l[3];  // tile-origin coordinate relative to the brick origin
+  {
+    const double zf = static_cast<double>(z0 + p.cz), yf = static_cast<double>(y0 + p.cy),
+                 xf = static_cast<double>(x0 + p.cx);
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const double c = coord_full(p.m + 4 * d, zf, yf, xf);
+      b0[d] = __double2int_rd(c + (g.neg[d] - 1e-6));
+      if (d == 2) b0[d] &= ~(kVec - 1);  // innermost TMA coordinate must be 16-byte aligned
+      bhi[d] = __double2int_rd(c + (g.pos[d] + 1e-6)) + 2;
+      c0l[d] = static_cast<float>(c - static_cast<double>(b0[d]));
+    }
+  }
+  const bool brick_ok = (bhi[0] - b0[0]) < g.BZ && (bhi[1] - b0[1]) < g.BY && (bhi[2] - b0[2]) < g.BX;
+
+  const int lx = threadIdx.x % kBrTX, ly = threadIdx.x / kBrTX;
+  const int x = x0 + lx;
+
+  if (!brick_ok) {  // host bound too tight for this tile (never expected): straight from global
+#pragma unroll
+    for (int c = 0; c < kBrCols; ++c) {
+      const int y = y0 + ly + c * kBrRowStep;
+      if (x < p.ox && y < p.oy)
+        for (int k = 0; k < nz; ++k)
+          p.dst[(static_cast<int64_t>(z0 + k) * p.oy + y) * p.dpitch + x] =
+              affine_sample_generic<T, ORDER, BOUNDARY, SCRUB>(p, z0 + k, y, x);
+    }
+    return;
+  }
+
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(&bar, static_cast<uint32_t>(g.bytes));
+    tma_load_3d(brick, &src_map, &bar, b0[2], b0[1], b0[0]);
+  }
+
+  // ---- per-axis constants in brick-local coordinates
+  // interior  <=>  |u - mid| <= half - kEdge   (both taps valid, away from every volume edge)
+  // outside   <=>  |u - mid| >  half + 0.5 + kEdge on some axis
+  float mcol[3][3], mid[3], half[3];
+  {
+    const int n[3] = {p.sz, p.sy, p.sx};
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) mcol[d][j] = g.mcol[3 * d + j];
+      half[d] = 0.5f * static_cast<float>(n[d] - 1);
+      mid[d] = half[d] - static_cast<float>(b0[d]);
+    }
+  }
+  const uint32_t es = static_cast<uint32_t>(sizeof(T));
+  const uint32_t row_b = static_cast<uint32_t>(g.BX) * es;
+  const uint32_t plane_b = static_cast<uint32_t>(g.BY) * row_b;
+  const int64_t out_plane = static_cast<int64_t>(p.oy) * p.dpitch;
+
+  mbar_wait(&bar, 0);
+
+#pragma unroll
+  for (int c = 0; c < kBrCols; ++c) {
+    const int yy = ly + c * kBrRowStep;
+    const int y = y0 + yy;
+    if (x >= p.ox || y >= p.oy) continue;
+    // column start (fp32, brick-local): tile origin + yy*col1 + lx*col2
+    float u0[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+      u0[d] = __fmaf_rn(static_cast<float>(lx), mcol[d][2],
+                        __fmaf_rn(static_cast<float>(yy), mcol[d][1], c0l[d]));
+    float* __restrict__ out = p.dst + (static_cast<int64_t>(z0) * p.oy + y) * p.dpitch + x;
+    uint32_t todo = 0;  // bit k: voxel k is not strictly interior -> handled after the hot loop
+#pragma unroll 2
+    float* __restrict__ o = out;
+    for (int k = 0; k < nz; ++k, o += out_plane) {
+      const float kf = static_cast<float>(k);
+      const float uz = __fmaf_rn(kf, mcol[0][0], u0[0]);
+      const float uy = __fmaf_rn(kf, mcol[1][0], u0[1]);
+      const float ux = __fmaf_rn(kf, mcol[2][0], u0[2]);
+      const bool interior = fabsf(uz - mid[0]) <= half[0] - kEdge &&
+                            fabsf(uy - mid[1]) <= half[1] - kEdge &&
+                            fabsf(ux - mid[2]) <= half[2] - kEdge;
+      if (!interior) {
+        todo |= 1u << k;
+        continue;
+      }
+      float v;
+      if (ORDER == 0) {
+        // round to nearest via the magic constant; the tie k+0.5 is re-decided exactly
+        const float rz = (uz + kMagic) - kMagic, ry = (uy + kMagic) - kMagic,
+                    rx = (ux + kMagic) - kMagic;
+        if (fabsf(fabsf(uz - rz) - 0.5f) < kEdge || fabsf(fabsf(uy - ry) - 0.5f) < kEdge ||
+            fabsf(fabsf(ux - rx) - 0.5f) < kEdge) {
+          todo |= 1u << k;
+          continue;
+        }
+        const uint32_t a = brick + static_cast<uint32_t>(static_cast<int>(rz)) * plane_b +
+                           static_cast<uint32_t>(static_cast<int>(ry)) * row_b +
+                           static_cast<uint32_t>(static_cast<int>(rx)) * es;
+        v = brick_elem<T>(a);
+        if (SCRUB && sizeof(T) == 4) v = scrub_value(v);
+      } else {
+        // floor via round-to-nearest of (u - 0.5): an exact integer u may land on u-1 with
+        // weight 1, which blends to the same value (both taps are valid in the interior)
+        const float tz = (uz - 0.5f) + kMagic, ty = (uy - 0.5f) + kMagic, tx = (ux - 0.5f) + kMagic;
+        const float wz = uz - (tz - kMagic), wy = uy - (ty - kMagic), wx = ux - (tx - kMagic);
+        const uint32_t a00 =
+            brick + static_cast<uint32_t>(__float_as_int(tz) - 0x4B400000) * plane_b +
+            static_cast<uint32_t>(__float_as_int(ty) - 0x4B400000) * row_b +
+            static_cast<uint32_t>(__float_as_int(tx) - 0x4B400000) * es;
+        const uint32_t a01 = a00 + row_b, a10 = a00 + plane_b, a11 = a10 + row_b;
+        const float v000 = brick_elem<T>(a00), v001 = brick_elem<T>(a00 + es);
+        const float v010 = brick_elem<T>(a01), v011 = brick_elem<T>(a01 + es);
+        const float v100 = brick_elem<T>(a10), v101 = brick_elem<T>(a10 + es);
+        const float v110 = brick_elem<T>(a11), v111 = brick_elem<T>(a11 + es);
+        const float bxw = 1.0f - wx, byw = 1.0f - wy;
+        const float r00 = __fmaf_rn(wx, v001, bxw * v000), r01 = __fmaf_rn(wx, v011, bxw * v010);
+        const float r10 = __fmaf_rn(wx, v101, bxw * v100), r11 = __fmaf_rn(wx, v111, bxw * v110);
+        const float q0 = __fmaf_rn(wy, r01, byw * r00), q1 = __fmaf_rn(wy, r11, byw * r10);
+        v = __fmaf_rn(wz, q1, (1.0f - wz) * q0);
+        // NaN/inf taps (possibly with zero weight): the exact path applies the scrub per tap
+        if (sizeof(T) == 4 && SCRUB && !(fabsf(v) <= FLT_MAX)) {
+          todo |= 1u << k;
+          continue;
+        }
+      }
+      st_global_cs(o, v);
+    }
+    // ---- voxels near a decision edge / outside the source: exact float64 path
+    while (todo) {
+      const int k = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const float kf = static_cast<float>(k);
+      const float dz = fabsf(__fmaf_rn(kf, mcol[0][0], u0[0]) - mid[0]);
+      const float dy = fabsf(__fmaf_rn(kf, mcol[1][0], u0[1]) - mid[1]);
+      const float dx = fabsf(__fmaf_rn(kf, mcol[2][0], u0[2]) - mid[2]);
+      const bool outside = dz > half[0] + 0.5f + kEdge || dy > half[1] + 0.5f + kEdge ||
+                           dx > half[2] + 0.5f + kEdge;
+      const float v = outside ? 0.0f
+                              : brick_sample_exact<T, ORDER, BOUNDARY, SCRUB>(
+                                    p, brick, b0[0], b0[1], b0[2], g.BY, g.BX, z0 + k, y, x);
+      st_global_cs(out + k * out_plane, v);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+static bool brick_geometry(const AffineParams& p, BrickGeom* g, size_t* smem_bytes) {
+  if (reinterpret_cast<uintptr_t>(p.src) % 16 != 0) return false;
+  if ((static_cast<int64_t>(p.spitch) * sizeof(T)) % 16 != 0) return false;
+  const int vec = 16 / sizeof(T);
+  const int t[3] = {kBrTZ - 1, kBrTY - 1, kBrTX - 1};
+  int ext[3];
+  for (int d = 0; d < 3; ++d) {
+    double neg = 0.0, pos = 0.0;
+    for (int j = 0; j < 3; ++j) {
+      const double v = p.m[4 * d + j] * t[j];
+      (v < 0.0 ? neg : pos) += v;
+    }
+    const double e = pos - neg;
+    if (!(e < 240.0)) return false;
+    ext[d] = static_cast<int>(e) + 5;
+    g->neg[d] = neg;
+    g->pos[d] = pos;
+  }
+  for (int i = 0; i < 9; ++i) g->mcol[i] = static_cast<float>(p.m[4 * (i / 3) + (i % 3)]);
+  // |coordinate| bound over the whole output (keeps the device-side int conversions defined)
+  for (int d = 0; d < 3; ++d) {
+    const double reach = fabs(p.m[4 * d]) * (p.oz + fabs((double)p.cz)) +
+                         fabs(p.m[4 * d + 1]) * (p.oy + fabs((double)p.cy)) +
+                         fabs(p.m[4 * d + 2]) * (p.ox + fabs((double)p.cx)) + fabs(p.m[4 * d + 3]);
+    if (!(reach < 1.0e9)) return false;
+  }
+  int BX = ext[2] + (vec - 1);
+  BX = (BX + vec - 1) / vec * vec;
+  if (ext[0] > 256 || ext[1] > 256 || BX > 256) return false;
+  const int64_t bytes = static_cast<int64_t>(ext[0]) * ext[1] * BX * sizeof(T);
+  if (bytes > 72 * 1024) return false;  // keep >= 3 CTAs per SM; larger footprints use the gather path
+  g->BZ = ext[0];
+  g->BY = ext[1];
+  g->BX = BX;
+  g->bytes = static_cast<int>(bytes);
+  *smem_bytes = static_cast<size_t>(bytes) + 128;
+  return true;
+}
+
+template <typename T, int ORDER, int BOUNDARY, bool SCRUB>
+static int launch_brick(const AffineParams& p, const BrickGeom& g, size_t smem_bytes,
+                        cudaStream_t stream) {
+  EncodeTiledFn encode = get_encode_tiled();
+  if (!encode) {
+    set_error("cuTensorMapEncodeTiled not available from the driver");
+    return B2_ERR_NO_DEVICE;
+  }
+  CUtensorMap map;
+  const cuuint64_t gdim[3] = {static_cast<cuuint64_t>(p.sx), static_cast<cuuint64_t>(p.sy),
+                              static_cast<cuuint64_t>(p.sz)};
+  const cuuint64_t gstride[2] = {static_cast<cuuint64_t>(p.spitch) * sizeof(T),
+                                 static_cast<cuuint64_t>(p.spitch) * p.sy * sizeof(T)};
+  const cuuint32_t box[3] = {static_cast<cuuint32_t>(g.BX), static_cast<cuuint32_t>(g.BY),
+                             static_cast<cuuint32_t>(g.BZ)};
+  const cuuint32_t estride[3] = {1, 1, 1};
+  const CUtensorMapDataType dt =
+      sizeof(T) == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  CUresult r = encode(&map, dt, 3, const_cast<void*>(p.src), gdim, gstride, box, estride,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (CUresult %d) for affine source (%d,%d,%d)", (int)r,
+              p.sz, p.sy, p.sx);
+    return B2_ERR_UNSUPPORTED;
+  }
+  const int tiles_z = (p.oz + kBrTZ - 1) / kBrTZ;
+  const int tiles_y = (p.oy + kBrTY - 1) / kBrTY;
+  const int tiles_x = (p.ox + kBrTX - 1) / kBrTX;
+  const int64_t tiles = static_cast<int64_t>(tiles_z) * tiles_y * tiles_x;
+  if (tiles > 2147483647LL) return affine_gather_launch(p, sizeof(T) == 2 ? B2_DTYPE_U16 : B2_DTYPE_F32, stream);
+  auto kern = affine_brick_kernel<T, ORDER, BOUNDARY, SCRUB>;
+  B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               static_cast<int>(smem_bytes)));
+  kern<<<static_cast<unsigned>(tiles), kBrThreads, smem_bytes, stream>>>(map, p, g, tiles_z, tiles_x);
+  B2_CUDA(cudaGetLastError());
+  count_launch();
+  return B2_OK;
+}
+
+template <typename T>
+static int brick_typed(const AffineParams& p, cudaStream_t stream, bool* eligible) {
+  BrickGeom g{};
+  size_t smem = 0;
+  *eligible = brick_geometry<T>(p, &g, &smem);
+  if (!*eligible) return B2_ERR_UNSUPPORTED;
+  const bool scrub = p.scrub && sizeof(T) == 4;
+#define B2_BR(ORD, BND)                                        \
+  (scrub ? launch_brick<T, ORD, BND, true>(p, g, smem, stream) \
+         : launch_brick<T, ORD, BND, false>(p, g, smem, stream))
+  if (p.order == 0)
+    return p.boundary == B2_BOUNDARY_CONSTANT ? B2_BR(0, B2_BOUNDARY_CONSTANT)
+                                              : B2_BR(0, B2_BOUNDARY_ITK);
+  return p.boundary == B2_BOUNDARY_CONSTANT ? B2_BR(1, B2_BOUNDARY_CONSTANT)
+                                            : B2_BR(1, B2_BOUNDARY_ITK);
+#undef B2_BR
+}
+
+int affine_brick_launch(const AffineParams& p, int src_dtype, cudaStream_t stream, bool* eligible) {
+  if (src_dtype == B2_DTYPE_U16) return brick_typed<uint16_t>(p, stream, eligible);
+  return brick_typed<float>(p, stream, eligible);
+}
+
+}  // namespace b2

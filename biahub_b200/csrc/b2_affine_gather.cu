@@ -5,29 +5,35 @@
 
 namespace b2 {
 
+constexpr int kGatherXPerThread = 4;
+
+// grid.x = output rows (z*oy + y), grid.y = chunks of 256*kGatherXPerThread voxels along x
 template <typename T, int ORDER, int BOUNDARY, bool SCRUB>
 __global__ void __launch_bounds__(256) affine_gather_kernel(const AffineParams p) {
-  const int64_t total = static_cast<int64_t>(p.oz) * p.oy * p.ox;
-  for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
-       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int x = static_cast<int>(idx % p.ox);
-    const int64_t r = idx / p.ox;
-    const int y = static_cast<int>(r % p.oy);
-    const int z = static_cast<int>(r / p.oy);
-    const float v = affine_sample_generic<T, ORDER, BOUNDARY, SCRUB>(p, z, y, x);
-    p.dst[r * p.dpitch + x] = v;
+  const int row = blockIdx.x;
+  const int z = row / p.oy;
+  const int y = row - z * p.oy;
+  double rp[3];
+  affine_row_part(p, z, y, rp);
+  float* __restrict__ out = p.dst + static_cast<int64_t>(row) * p.dpitch;
+  const int x0 = blockIdx.y * (256 * kGatherXPerThread) + threadIdx.x;
+#pragma unroll
+  for (int i = 0; i < kGatherXPerThread; ++i) {
+    const int x = x0 + i * 256;
+    if (x < p.ox) out[x] = affine_sample_row<T, ORDER, BOUNDARY, SCRUB>(p, rp, x);
   }
 }
 
 template <typename T, int ORDER, int BOUNDARY>
 static int launch_gather_scrub(const AffineParams& p, cudaStream_t stream) {
-  int sms = 148;
-  sm_count(&sms);
-  const int64_t total = static_cast<int64_t>(p.oz) * p.oy * p.ox;
-  if (total == 0) return B2_OK;
-  const int64_t want = (total + 255) / 256;
-  const int64_t cap = static_cast<int64_t>(sms) * 64;
-  const int grid = static_cast<int>(want < cap ? want : cap);
+  const int64_t rows = static_cast<int64_t>(p.oz) * p.oy;
+  if (rows == 0 || p.ox == 0) return B2_OK;
+  const int xchunks = (p.ox + 256 * kGatherXPerThread - 1) / (256 * kGatherXPerThread);
+  if (rows > 2147483647LL || xchunks > 65535) {
+    set_error("affine3d: output too large for the gather kernel grid");
+    return B2_ERR_INVALID;
+  }
+  const dim3 grid(static_cast<unsigned>(rows), static_cast<unsigned>(xchunks), 1);
   if (p.scrub && sizeof(T) == 4)
     affine_gather_kernel<T, ORDER, BOUNDARY, true><<<grid, 256, 0, stream>>>(p);
   else
@@ -112,11 +118,13 @@ int affine_device(const void* src, int src_dtype, int64_t sz, int64_t sy, int64_
 
   if (path != B2_PATH_GATHER) {
     bool eligible = false;
-    const int rc = affine_zsep_launch(p, src_dtype, stream, &eligible);
+    int rc = affine_zsep_launch(p, src_dtype, stream, &eligible);
+    if (eligible) return rc;
+    rc = affine_brick_launch(p, src_dtype, stream, &eligible);  // generic matrices
     if (eligible) return rc;
     if (path == B2_PATH_TMA) {
-      set_error("affine3d: TMA path not eligible (needs a z-separable matrix with m00 > 0, "
-                "16-byte aligned source rows and a plane brick that fits shared memory)");
+      set_error("affine3d: TMA paths not eligible (need 16-byte aligned source rows and a "
+                "back-projected tile brick that fits shared memory)");
       return B2_ERR_UNSUPPORTED;
     }
   }

@@ -71,8 +71,8 @@ __device__ __noinline__ void zsep_tile_from_global(const AffineParams& p, int y0
 
 template <typename T, int ORDER, int BOUNDARY, bool SCRUB>
 __global__ void __launch_bounds__(kZsThreads, 3)
-    affine_zsep_kernel(const __grid_constant__ CUtensorMap src_map, const AffineParams p,
-                       const ZsepGeom g) {
+    affine_zsep_kernel(const __grid_constant__ CUtensorMap src_map,
+                       const __grid_constant__ AffineParams p, const ZsepGeom g) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[kZsStages];
   __shared__ uint64_t empty_bar[kZsStages];

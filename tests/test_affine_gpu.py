@@ -107,13 +107,46 @@ def test_tma_path_is_taken_and_matches_gather(mname):
                 assert (a - b).abs().max().item() <= 2e-6 * 4095.0  # 4-weight vs nested-lerp rounding
 
 
-def test_generic_matrix_not_tma_eligible():
+def test_unaligned_rows_not_tma_eligible():
     from biahub_b200 import _cabi, affine_warp
     from biahub_b200._cabi import B2Unsupported
 
-    vol = _vol((8, 64, 64), seed=1)
+    vol = _vol((8, 64, 63), seed=1)          # 63 floats per row: rows are not 16-byte aligned
     with pytest.raises(B2Unsupported):
         affine_warp(_to_cuda(vol), MATRICES["generic"](vol.shape), vol.shape, _path=_cabi.PATH_TMA)
+    got = affine_warp(_to_cuda(vol), MATRICES["generic"](vol.shape), vol.shape).cpu().numpy()
+    _compare(got, ao.affine_oracle_numpy(vol, MATRICES["generic"](vol.shape), vol.shape, 1, "itk"), 1)
+
+
+@pytest.mark.parametrize("mname", ["generic", "zflip", "fliplr_tilt", "big_tilt"])
+def test_generic_brick_kernel(mname):
+    """Non z-separable matrices take the 3-D TMA brick kernel (PATH_TMA raises otherwise): order 0
+    bit-exact vs the float64 oracle, order 1 within tolerance, both boundary rules, uint16 too."""
+    import torch
+
+    from biahub_b200 import _cabi, affine_warp
+
+    shape = (28, 120, 200)
+    mats = dict(MATRICES)
+    mats["fliplr_tilt"] = lambda s: MATRICES["fliplr"](s) @ MATRICES["generic"](s)
+    th = np.radians(12.0)
+    mats["big_tilt"] = lambda s: np.array([[np.cos(th), 0, -np.sin(th), 8.0], [0, 1, 0, -0.5],
+                                           [np.sin(th), 0, np.cos(th), -3.0], [0, 0, 0, 1.0]])
+    M = mats[mname](shape)
+    out_shape = (30, 116, 204)
+    vol = _vol(shape, seed=17, nan_frac=0.001)
+    u16 = np.random.default_rng(3).integers(0, 65536, size=shape, dtype=np.uint16)
+    for boundary in ("constant", "itk"):
+        for order in (0, 1):
+            want = ao.affine_oracle_numpy(vol, M, out_shape, order, boundary)
+            got = affine_warp(_to_cuda(vol), M, out_shape, order=order, boundary=boundary,
+                              _path=_cabi.PATH_TMA)
+            torch.cuda.synchronize()
+            _compare(got.cpu().numpy(), want, order, name=f"{mname}/{order}/{boundary}")
+            want = ao.affine_oracle_numpy(u16, M, out_shape, order, boundary)
+            got = affine_warp(_to_cuda(u16), M, out_shape, order=order, boundary=boundary,
+                              _path=_cabi.PATH_TMA)
+            _compare(got.cpu().numpy(), want, order, rng=65535.0, name=f"{mname}/u16/{order}/{boundary}")
 
 
 def test_uint16_source_and_crop():
