@@ -43,7 +43,7 @@ WORKLOADS = {
     # BASELINE.json configs[1]: mantis-sized deskew, average_n_slices=3, uint16 (T=8,C=2,800,300,2048)
     "deskew_c2": dict(kind="deskew", shape=(800, 300, 2048), dtype="uint16", units=16,
                       ls_angle_deg=30.0, px_to_scan_ratio=0.386, keep_overhang=False,
-                      average_n_slices=3, e2e_units=4,
+                      average_n_slices=3, e2e_units=2,
                       desc="C2 mantis deskew uint16 (T=8,C=2,Z=800,Y=300,X=2048) theta=30 px=0.386 N=3 crop"),
     # configs[0]
     "deskew_c1": dict(kind="deskew", shape=(256, 256, 512), dtype="uint16", units=16,
@@ -334,6 +334,25 @@ def run_b200(args, w, rank, world, local_rank):
     esz = 2 if w["dtype"] == "uint16" else 4
     check = (float(h_out[0].ravel()[:: max(1, h_out[0].size // 1000)].astype(np.float64).sum())
              if e2e_units else None)
+    # same call with ordinary (pageable) numpy arrays in and a fresh array out: what the
+    # reference's process_single_position hands over; staged through the library's pinned rings
+    pageable_value = None
+    if e2e_units and rank == 0 and world == 1 and w["kind"] in ("deskew", "register", "stabilize"):
+        src_pg = np.array(h_in[0], copy=True)
+        for rep in range(2):
+            t0 = time.perf_counter()
+            if w["kind"] == "deskew":
+                res = b2._fast_deskew_czyx(src_pg[None], device=f"cuda:{local_rank}",
+                                           ls_angle_deg=w["ls_angle_deg"],
+                                           px_to_scan_ratio=w["px_to_scan_ratio"],
+                                           keep_overhang=w["keep_overhang"],
+                                           average_n_slices=w["average_n_slices"])
+            else:
+                res = b2.affine_warp(src_pg, mats[0], out_shape, order=1, boundary="itk",
+                                     device=local_rank)
+            dt_pg = time.perf_counter() - t0
+        pageable_value = out_vox / dt_pg / 1e9
+        del res, src_pg
 
     peak, peak_src = read_peaks()
     achieved = bytes_unit / (launch_ms * 1e-3) / 1e9
@@ -361,7 +380,8 @@ def run_b200(args, w, rank, world, local_rank):
                 "steps": e2e_steps, "units_per_step_per_gpu": e2e_units,
                 "api": ("biahub_b200._fast_deskew_czyx" if w["kind"] == "deskew" else "biahub_b200.affine_warp (apply_affine_transform/apply_stabilization_transform body)")
                        + " with pinned host in/out -> b2h_* C-ABI",
-                "gpu_launches": int(launches_e2e), "checksum": check},
+                "gpu_launches": int(launches_e2e), "checksum": check,
+                "pageable_value": None if pageable_value is None else round(pageable_value, 3)},
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                      "frac": round(achieved / peak, 4), "traffic": None,
                      "kernel": {"deskew": "deskew_tma_kernel", "chain": "deskew_tma_kernel + affine_zsep_kernel (bytes and time of both)"}.get(w["kind"], "affine_gather_kernel" if w.get("generic") else "affine_zsep_kernel"),

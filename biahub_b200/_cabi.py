@@ -27,7 +27,7 @@ ERR_UNSUPPORTED = 2
 ERR_NO_DEVICE = 3
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, "_lib", "libbiahub_b200.so")
+LIB_PATH = os.environ.get("BIAHUB_B200_LIB") or os.path.join(_PKG_DIR, "_lib", "libbiahub_b200.so")
 
 EXPORTS = (
     "b2_abi_version", "b2_last_error", "b2_device_count", "b2_check_device", "b2_deskew",

@@ -323,16 +323,10 @@ static bool zsep_geometry(const AffineParams& p, ZsepGeom* g, size_t* smem_bytes
   const int BY = static_cast<int>(ey) + 5;
   int BX = static_cast<int>(ex) + 5 + (vec - 1);  // + alignment slack of the brick origin
   BX = (BX + vec - 1) / vec * vec;
-  // a row pitch that is a multiple of 32 banks keeps the lanes of a warp (which walk along x
-  // and change row every few lanes under rotation) on distinct banks; take it when it fits
-  const int bank_elems = 128 / static_cast<int>(sizeof(T));
-  const int BX_banked = (BX + bank_elems - 1) / bank_elems * bank_elems;
+  // (a bank-aligned row pitch was measured and makes no difference: the lanes of a warp span ~34
+  // columns under a 1.07x scale, so every LDS costs 2 wavefronts either way and the kernel is not
+  // bound by shared-memory bandwidth)
   auto stage_of = [&](int bx) { return (BY * bx * static_cast<int>(sizeof(T)) + 127) / 128 * 128; };
-  static const bool use_banked = [] {
-    const char* e = getenv("B2_ZS_BANK");
-    return e ? atoi(e) != 0 : false;
-  }();
-  if (use_banked && BX_banked <= 256 && stage_of(BX_banked) * kZsStages <= 56 * 1024) BX = BX_banked;
   if (BY > 256 || BX > 256) return false;
   const int stage = stage_of(BX);
   if (stage * kZsStages > 96 * 1024) return false;
