@@ -174,8 +174,8 @@ __global__ void __launch_bounds__(kBrThreads, 3)
                         __fmaf_rn(static_cast<float>(yy), mcol[d][1], c0l[d]));
     float* __restrict__ out = p.dst + (static_cast<int64_t>(z0) * p.oy + y) * p.dpitch + x;
     uint32_t todo = 0;  // bit k: voxel k is not strictly interior -> handled after the hot loop
-#pragma unroll 2
     float* __restrict__ o = out;
+#pragma unroll 2
     for (int k = 0; k < nz; ++k, o += out_plane) {
       const float kf = static_cast<float>(k);
       const float uz = __fmaf_rn(kf, mcol[0][0], u0[0]);

@@ -102,7 +102,13 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
 
 __device__ __forceinline__ void st_global_cs(float* p, float v) {
   // streaming store: the output is written once and never re-read by this kernel
+#if defined(B2_STORE_PLAIN)
+  *p = v;
+#elif defined(B2_STORE_CG)
+  __stcg(p, v);
+#else
   __stcs(p, v);
+#endif
 }
 __device__ __forceinline__ void st_global_cs4(float* p, float4 v) {
   asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y),

@@ -1,0 +1,44 @@
+"""Sweep deskew launch configurations (env-selected) over N / dtype / px; prints frac of HBM peak."""
+import os, subprocess, sys, json
+CONFIGS = {
+  "default plan":         dict(),
+  "A yfast TX128":        dict(B2_DESKEW_TX="128", B2_DESKEW_STAGE="0", B2_DESKEW_XFAST="0"),
+}
+INNER = r'''
+import sys; sys.path.insert(0, "/root/repo")
+import torch, json, biahub_b200 as b2
+dev = torch.device("cuda"); g = torch.Generator(device=dev); g.manual_seed(0)
+out = {}
+for dtype in ("u16", "f32"):
+    if dtype == "u16":
+        srcs = [torch.randint(0, 65536, (800, 300, 2048), generator=g, device=dev, dtype=torch.int32).to(torch.uint16) for _ in range(4)]
+    else:
+        srcs = [torch.rand((800, 300, 2048), generator=g, device=dev) * 4095 for _ in range(4)]
+    for px in (0.386, 0.755):
+        for N in (1, 2, 3, 4):
+            for _ in range(2):
+                for s in srcs: o = b2.fast_deskew_zyx(s, 30.0, px, False, N)
+            torch.cuda.synchronize()
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                for s in srcs: o = b2.fast_deskew_zyx(s, 30.0, px, False, N)
+            e1.record(); torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 20
+            byt = srcs[0].numel() * srcs[0].element_size() + o.numel() * 4
+            out[f"{dtype} px{px} N{N}"] = round(byt / ms / 1e6 / 6534.1, 3)
+    del srcs
+print(json.dumps(out))
+'''
+res = {}
+for name, env in CONFIGS.items():
+    e = dict(os.environ); e.update(env)
+    r = subprocess.run([sys.executable, "-c", INNER], capture_output=True, text=True, env=e, timeout=600)
+    try:
+        res[name] = json.loads(r.stdout.strip().splitlines()[-1])
+    except Exception:
+        res[name] = {"error": (r.stderr or r.stdout)[-300:]}
+keys = list(next(iter(res.values())).keys())
+print(f"{'case':18s} " + " ".join(f"{n[:12]:>13s}" for n in res))
+for k in keys:
+    print(f"{k:18s} " + " ".join(f"{res[n].get(k, float('nan')):13}" for n in res))
