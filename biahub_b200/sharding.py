@@ -16,6 +16,8 @@ from __future__ import annotations
 
 import inspect
 import os
+import queue
+import threading
 from typing import Callable, Iterable, Sequence
 
 
@@ -57,4 +59,78 @@ def run_units(func: Callable, read_unit: Callable, write_unit: Callable, units: 
             call_kwargs["input_time_index"] = t
         write_unit(p, t, c, func(block, **call_kwargs))
         done += 1
+    return done
+
+
+def run_units_overlapped(func: Callable, read_unit: Callable, write_unit: Callable, units: Iterable,
+                         prefetch: int = 2, **kwargs):
+    """``run_units`` as a three-stage pipeline: a reader thread decodes the next ``prefetch``
+    units (zarr chunk I/O) and a writer thread stores finished ones while the calling thread
+    keeps the GPU busy.  The compute call spends its time inside libbiahub_b200 (ctypes releases
+    the GIL; the library itself overlaps H2D / kernel / D2H on three CUDA streams), so host I/O,
+    PCIe and kernels all run concurrently.  Units complete in order; the first exception of any
+    stage is re-raised after the other stages have been stopped."""
+    kwargs = dict(kwargs)
+    kwargs.pop("extra_metadata", None)
+    wants_time = "input_time_index" in inspect.signature(func).parameters
+    units = list(units)
+    q_in: "queue.Queue" = queue.Queue(maxsize=max(1, int(prefetch)))
+    q_out: "queue.Queue" = queue.Queue(maxsize=max(1, int(prefetch)))
+    errors = []
+    stop = threading.Event()
+
+    def reader():
+        try:
+            for u in units:
+                if stop.is_set():
+                    break
+                q_in.put((u, read_unit(*u)))
+        except BaseException as exc:  # noqa: BLE001 - re-raised on the caller's thread
+            errors.append(exc)
+        finally:
+            q_in.put(None)
+
+    def writer():
+        try:
+            while True:
+                item = q_out.get()
+                if item is None:
+                    break
+                (p, t, c), out = item
+                write_unit(p, t, c, out)
+        except BaseException as exc:  # noqa: BLE001
+            errors.append(exc)
+            stop.set()
+            while q_out.get() is not None:  # drain so the producer never blocks
+                pass
+
+    tr = threading.Thread(target=reader, name="b2-read", daemon=True)
+    tw = threading.Thread(target=writer, name="b2-write", daemon=True)
+    tr.start()
+    tw.start()
+    done = 0
+    try:
+        while True:
+            item = q_in.get()
+            if item is None or stop.is_set():
+                break
+            (p, t, c), block = item
+            call_kwargs = dict(kwargs)
+            if wants_time and "input_time_index" not in call_kwargs:
+                call_kwargs["input_time_index"] = t
+            q_out.put(((p, t, c), func(block, **call_kwargs)))
+            done += 1
+    except BaseException as exc:  # noqa: BLE001
+        errors.append(exc)
+    finally:
+        stop.set()
+        q_out.put(None)
+        while tr.is_alive():  # unblock a reader stuck on a full queue
+            try:
+                q_in.get_nowait()
+            except queue.Empty:
+                tr.join(timeout=0.05)
+        tw.join()
+    if errors:
+        raise errors[0]
     return done

@@ -34,7 +34,8 @@ def full(wl):
 
 def sass():
     out = ["# SASS evidence (cuobjdump -sass of the built objects): mnemonic counts per kernel family"]
-    for obj, pat in (("b2_deskew.o", "deskew_tma_kernelItLi3"), ("b2_affine_zsep.o", "affine_zsep_kernelIfLi1ELi1ELb1")):
+    for obj, pat in (("b2_deskew.o", "deskew_tma_kernelItLi3ELi128"), ("b2_deskew.o", "deskew_stage_kernelILi1ELi256"),
+                     ("b2_affine_zsep.o", "affine_zsep_kernelIfLi1ELi1ELb1"), ("b2_affine_brick.o", "affine_brick_kernelIfLi1ELi1ELb1")):
         p = os.path.join(ROOT, "biahub_b200", "_lib", "obj", obj)
         txt = subprocess.run(["cuobjdump", "-sass", p], capture_output=True, text=True).stdout
         m = re.search(r"Function : (\S*%s\S*)(.*?)(?=Function :|\Z)" % pat, txt, re.S)
@@ -49,7 +50,7 @@ def sass():
         out.append("  texture instructions (TEX/TLD): %d" % sum(v for k, v in cnt.items() if k.startswith(("TEX", "TLD"))))
     return "\n".join(out)
 
-for wl in ("deskew_c2", "register_c3", "stabilize_c4"):
+for wl in ("deskew_c2", "deskew_c1", "register_c3", "stabilize_c4", "register_generic"):
     parts = [p for p in (launches(wl), full(wl)) if p]
     if parts:
         with open(os.path.join(ROOT, "profiles", f"{rnd}_{wl}.txt"), "w") as fh:

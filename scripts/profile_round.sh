@@ -4,22 +4,17 @@
 set -u
 R=${1:-r1}
 OUT=gpurun_out
-for wl in deskew_c2 register_c3 stabilize_c4; do
+for wl in deskew_c2 deskew_c1 register_c3 stabilize_c4 register_generic; do
   CMD="python bench.py --workload $wl --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --units 2"
   $CMD > $OUT/plain_${wl}_${R}.log 2>&1 && \
   ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv \
       --log-file $OUT/launches_${wl}_${R}.csv $CMD > $OUT/ncu_launches_${wl}_${R}.log 2>&1
 done
-CMD="python bench.py --workload deskew_c2 --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --units 2"
-$CMD > $OUT/plain_full_deskew_${R}.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:deskew_tma -s 2 -c 1 \
-    -o $OUT/prof_deskew_c2_${R} $CMD > $OUT/ncu_full_deskew_${R}.log 2>&1
-CMD="python bench.py --workload register_c3 --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --units 2"
-$CMD > $OUT/plain_full_register_${R}.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:affine_zsep -s 2 -c 1 \
-    -o $OUT/prof_register_c3_${R} $CMD > $OUT/ncu_full_register_${R}.log 2>&1
-CMD="python bench.py --workload stabilize_c4 --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --units 2"
-$CMD > $OUT/plain_full_stabilize_${R}.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:affine_zsep -s 2 -c 1 \
-    -o $OUT/prof_stabilize_c4_${R} $CMD > $OUT/ncu_full_stabilize_${R}.log 2>&1
-ls -la $OUT | tail -20
+for pair in "deskew_c2:deskew_" "deskew_c1:deskew_" "register_c3:affine_zsep" "stabilize_c4:affine_zsep" "register_generic:affine_brick"; do
+  wl=${pair%%:*}; pat=${pair##*:}
+  CMD="python bench.py --workload $wl --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --units 2"
+  $CMD > $OUT/plain_full_${wl}_${R}.log 2>&1 && \
+  ncu --set full --clock-control none --import-source on -k regex:$pat -s 2 -c 1 \
+      -o $OUT/prof_${wl}_${R} $CMD > $OUT/ncu_full_${wl}_${R}.log 2>&1
+done
+ls $OUT | grep "_${R}" | wc -l

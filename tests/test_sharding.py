@@ -94,3 +94,63 @@ def test_world_size_2_gloo():
     assert len(gathered[0]) == len(gathered[1]) == 6
     for (p, t, c), v in merged.items():
         assert v == 8 * (p * 100 + t * 10 + c)
+
+
+def test_run_units_overlapped_pipelines_and_orders():
+    import threading
+    import time
+
+    units = sharding.enumerate_units(1, range(6), [0])
+    log, written = [], []
+    lock = threading.Lock()
+
+    def read(p, t, c):
+        time.sleep(0.05)
+        with lock:
+            log.append(("r", t, time.perf_counter()))
+        return np.full((1, 1, 1, 2), t, np.float32)
+
+    def compute(czyx, input_time_index, gain):
+        time.sleep(0.05)
+        assert czyx[0, 0, 0, 0] == input_time_index
+        return czyx * gain
+
+    def write(p, t, c, out):
+        time.sleep(0.05)
+        written.append((t, float(out[0, 0, 0, 0])))
+
+    t0 = time.perf_counter()
+    n = sharding.run_units_overlapped(compute, read, write, units, prefetch=2, gain=2.0,
+                                      extra_metadata={"ignored": True})
+    dt = time.perf_counter() - t0
+    assert n == 6
+    assert written == [(t, 2.0 * t) for t in range(6)]        # in order, every unit once
+    assert dt < 0.75 * (6 * 0.15)                              # stages overlapped (serial = 0.9 s)
+
+
+def test_run_units_overlapped_propagates_errors():
+    units = sharding.enumerate_units(1, range(5), [0])
+
+    def bad_compute(czyx):
+        if czyx[0, 0, 0, 0] == 2:
+            raise RuntimeError("kernel failed")
+        return czyx
+
+    with pytest.raises(RuntimeError, match="kernel failed"):
+        sharding.run_units_overlapped(bad_compute, lambda p, t, c: np.full((1, 1, 1, 1), t),
+                                      lambda p, t, c, o: None, units)
+
+    def bad_read(p, t, c):
+        if t == 3:
+            raise OSError("chunk missing")
+        return np.zeros((1, 1, 1, 1))
+
+    with pytest.raises(OSError, match="chunk missing"):
+        sharding.run_units_overlapped(lambda x: x, bad_read, lambda p, t, c, o: None, units)
+
+    def bad_write(p, t, c, o):
+        raise IOError("disk full")
+
+    with pytest.raises(IOError, match="disk full"):
+        sharding.run_units_overlapped(lambda x: x, lambda p, t, c: np.zeros((1, 1, 1, 1)),
+                                      bad_write, units)
