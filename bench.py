@@ -43,16 +43,16 @@ WORKLOADS = {
     # BASELINE.json configs[1]: mantis-sized deskew, average_n_slices=3, uint16 (T=8,C=2,800,300,2048)
     "deskew_c2": dict(kind="deskew", shape=(800, 300, 2048), dtype="uint16", units=16,
                       ls_angle_deg=30.0, px_to_scan_ratio=0.386, keep_overhang=False,
-                      average_n_slices=3, e2e_units=2,
+                      average_n_slices=3, e2e_units=2, ncu_traffic=2.3365e9,
                       desc="C2 mantis deskew uint16 (T=8,C=2,Z=800,Y=300,X=2048) theta=30 px=0.386 N=3 crop"),
     # configs[0]
     "deskew_c1": dict(kind="deskew", shape=(256, 256, 512), dtype="uint16", units=16,
                       ls_angle_deg=30.0, px_to_scan_ratio=0.386, keep_overhang=False,
-                      average_n_slices=1, e2e_units=8,
+                      average_n_slices=1, e2e_units=8, ncu_traffic=2.248e8,
                       desc="C1 deskew uint16 (Z=256,Y=256,X=512) theta=30 px=0.386 N=1 crop; 16 distinct volumes"),
     # configs[2]
     "register_c3": dict(kind="register", shape=(120, 2048, 2048), dtype="float32", units=8,
-                        e2e_units=2,
+                        e2e_units=2, ncu_traffic=4.1942e9,
                         desc="C3 register float32 (Z=120,Y=2048,X=2048) rot 7.3deg scale 1.07 shift (0.4,3.25,-11.5) order 1"),
     # C3 geometry with a NON z-separable matrix (small 3-D rotation about Y and X on top of C3):
     # exercises the generic path
@@ -61,7 +61,7 @@ WORKLOADS = {
                              desc="C3 shape float32 (120,2048,2048), generic 3-D affine (C3 matrix + 0.5/0.3 deg out-of-plane rotations), order 1"),
     # configs[3]
     "stabilize_c4": dict(kind="stabilize", shape=(64, 2048, 2048), dtype="float32", units=16,
-                         e2e_units=4,
+                         e2e_units=4, ncu_traffic=2.1138e9,
                          desc="C4 stabilize float32 (Z=64,Y=2048,X=2048) fractional XYZ translations"),
     # configs[4] (per position/timepoint unit): deskew (C2 parameters) then register the deskewed
     # float32 (100,2048,1813) volume onto the same shape, intermediate resident in HBM
@@ -111,9 +111,16 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def wait_first_sample(self, timeout=5.0):
+        """nvidia-smi takes ~1 s to start on an 8-GPU box: wait until it reports."""
+        t0 = time.perf_counter()
+        while self.proc is not None and not self.rows and time.perf_counter() - t0 < timeout:
+            time.sleep(0.02)
+        return time.perf_counter()
+
+    def stop(self, since=0.0):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -124,7 +131,9 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for row in self.rows:
+        for stamp, row in self.rows:
+            if stamp < since:
+                continue
             parts = [p.strip() for p in row.split(",")]
             if len(parts) < 6:
                 continue
@@ -204,6 +213,8 @@ def run_b200(args, w, rank, world, local_rank):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    from biahub_b200._device import bind_to_gpu_numa
+    numa = bind_to_gpu_numa(local_rank) if world > 1 else {"numa_node": None}
     _cabi.require_device(local_rank)
     dist = None
     if world > 1:
@@ -257,11 +268,16 @@ def run_b200(args, w, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        device_step()
-    barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
+    load_start = sampler.wait_first_sample()
+    warm_done = 0
+    while warm_done < max(args.warmup, 3) or time.perf_counter() - load_start < 0.5:
+        device_step()          # untimed warm-up: at least W steps and 0.5 s of load for the sampler
+        warm_done += 1
+        if warm_done % 4 == 0:
+            torch.cuda.synchronize()
+    barrier()
     launches0 = _cabi.launch_count()
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
@@ -270,7 +286,7 @@ def run_b200(args, w, rank, world, local_rank):
         device_step()
     e1.record()
     barrier()
-    clocks = sampler.stop()
+    clocks = sampler.stop(since=load_start + 0.2)
     kernel_launches = _cabi.launch_count() - launches0
     ms_total = e0.elapsed_time(e1)
     t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
@@ -380,10 +396,13 @@ def run_b200(args, w, rank, world, local_rank):
                 "steps": e2e_steps, "units_per_step_per_gpu": e2e_units,
                 "api": ("biahub_b200._fast_deskew_czyx" if w["kind"] == "deskew" else "biahub_b200.affine_warp (apply_affine_transform/apply_stabilization_transform body)")
                        + " with pinned host in/out -> b2h_* C-ABI",
-                "gpu_launches": int(launches_e2e), "checksum": check,
+                "gpu_launches": int(launches_e2e), "checksum": check, "numa_node": numa.get("numa_node"),
                 "pageable_value": None if pageable_value is None else round(pageable_value, 3)},
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                     "frac": round(achieved / peak, 4), "traffic": None,
+                     "frac": round(achieved / peak, 4),
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the
+                     # committed ncu --set full capture of this workload (profiles/r1_*.txt)
+                     "traffic": w.get("ncu_traffic"),
                      "kernel": {"deskew": "deskew_tma_kernel", "chain": "deskew_tma_kernel + affine_zsep_kernel (bytes and time of both)"}.get(w["kind"], "affine_gather_kernel" if w.get("generic") else "affine_zsep_kernel"),
                      "algorithmic_bytes_per_launch": int(bytes_unit),
                      "launch_ms": round(launch_ms, 4), "peak_source": peak_src},

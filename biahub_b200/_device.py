@@ -150,3 +150,43 @@ def check_out(out, shape):
             and out.flags.c_contiguous):
         raise ValueError(f"out must be a C-contiguous float32 array of shape {tuple(shape)}")
     return out
+
+
+def bind_to_gpu_numa(device: int) -> dict:
+    """Pin the calling process to the CPUs of the NUMA node the GPU hangs off, so that pinned
+    staging buffers allocated afterwards (first touch) and the host copy threads are local to the
+    GPU's PCIe root.  On multi-socket hosts remote pinned memory is what limits 8-GPU end-to-end
+    throughput.  Best effort: returns what was done, never raises."""
+    info = {"device": int(device), "numa_node": None, "cpus": None}
+    try:
+        import torch
+
+        bdf = torch.cuda.get_device_properties(int(device)).pci_bus_id if hasattr(
+            torch.cuda.get_device_properties(int(device)), "pci_bus_id") else None
+        if bdf is None:
+            import ctypes
+
+            buf = ctypes.create_string_buffer(32)
+            rt = ctypes.CDLL("libcudart.so.12")
+            if rt.cudaDeviceGetPCIBusId(buf, 32, int(device)) != 0:
+                return info
+            bdf = buf.value.decode()
+        bdf = bdf.lower()
+        if len(bdf.split(":")[0]) == 8:      # 00000000:17:00.0 -> 0000:17:00.0
+            bdf = bdf[4:]
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as fh:
+            node = int(fh.read().strip())
+        if node < 0:
+            return info
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as fh:
+            cpus = set()
+            for part in fh.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info.update(numa_node=node, cpus=len(allowed))
+    except Exception:  # noqa: BLE001 - best effort only
+        pass
+    return info
