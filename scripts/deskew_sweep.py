@@ -2,7 +2,12 @@
 import os, subprocess, sys, json
 CONFIGS = {
   "default plan":         dict(),
-  "A yfast TX128":        dict(B2_DESKEW_TX="128", B2_DESKEW_STAGE="0", B2_DESKEW_XFAST="0"),
+  "A reg y128":           dict(B2_DESKEW_TX="128", B2_DESKEW_STAGE="0", B2_DESKEW_XFAST="0"),
+  "B reg x256":           dict(B2_DESKEW_TX="256", B2_DESKEW_STAGE="0", B2_DESKEW_XFAST="1"),
+  "C reg x128":           dict(B2_DESKEW_TX="128", B2_DESKEW_STAGE="0", B2_DESKEW_XFAST="1"),
+  "D reg y256":           dict(B2_DESKEW_TX="256", B2_DESKEW_STAGE="0", B2_DESKEW_XFAST="0"),
+  "E stage x256":         dict(B2_DESKEW_TX="256", B2_DESKEW_STAGE="1", B2_DESKEW_XFAST="1"),
+  "F stage x128":         dict(B2_DESKEW_TX="128", B2_DESKEW_STAGE="1", B2_DESKEW_XFAST="1"),
 }
 INNER = r'''
 import sys; sys.path.insert(0, "/root/repo")
