@@ -18,12 +18,11 @@
 
 namespace b2 {
 
-constexpr int kZsTY = 16;
+// tile height kZsTY is a template parameter (16 or 32 rows -> 4 or 8 output points per thread)
 constexpr int kZsTX = 64;
 constexpr int kZsConsumers = 256;
 constexpr int kZsThreads = kZsConsumers + 32;  // + one producer warp
 constexpr int kZsStages = 4;
-constexpr int kZsPPT = (kZsTY * kZsTX) / kZsConsumers;  // output points per consumer thread
 constexpr int kZsRowsPerPass = kZsConsumers / kZsTX;
 constexpr int kZsMaxChunk = 128;  // output planes per CTA (size of the z tap table)
 
@@ -55,7 +54,7 @@ __device__ __forceinline__ double coord_yx(double yf, double xf, const double* m
 
 // Rare path: the host-side bound on the brick size was too tight for this tile (never expected):
 // every thread of the CTA resamples the tile straight from global memory.
-template <typename T, int ORDER, int BOUNDARY, bool SCRUB>
+template <typename T, int ORDER, int BOUNDARY, bool SCRUB, int kZsTY>
 __device__ __noinline__ void zsep_tile_from_global(const AffineParams& p, int y0, int x0, int zb,
                                                    int ze) {
   const int n = (ze - zb) * kZsTY * kZsTX;
@@ -69,18 +68,23 @@ __device__ __noinline__ void zsep_tile_from_global(const AffineParams& p, int y0
   }
 }
 
-template <typename T, int ORDER, int BOUNDARY, bool SCRUB>
-__global__ void __launch_bounds__(kZsThreads, 3)
+template <typename T, int ORDER, int BOUNDARY, bool SCRUB, int kZsTY>
+__global__ void __launch_bounds__(kZsThreads) __maxnreg__(kZsTY == 16 ? 72 : 112)
     affine_zsep_kernel(const __grid_constant__ CUtensorMap src_map,
                        const __grid_constant__ AffineParams p, const ZsepGeom g) {
+  constexpr int kZsPPT = (kZsTY * kZsTX) / kZsConsumers;  // output points per consumer thread
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t full_bar[kZsStages];
-  __shared__ uint64_t empty_bar[kZsStages];
   // per output plane of this CTA: {i0 (or -1 when outside), i1, bits(w0), bits(w1)}
   __shared__ int4 ztab[kZsMaxChunk];
 
   constexpr int kVec = 16 / static_cast<int>(sizeof(T));
-  const uint32_t stage0 = (smem_u32(smem_raw) + 127u) & ~127u;
+  // dynamic shared memory: [full barriers | empty barriers | pad to 128 B] [stage ring]; all
+  // addresses derive from ONE register (a static __shared__ barrier array makes the compiler
+  // re-derive the shared-window address with S2R/LEA inside the plane loop)
+  const uint32_t bars = (smem_u32(smem_raw) + 127u) & ~127u;
+  const uint32_t full0 = bars;
+  const uint32_t empty0 = bars + 8u * kZsStages;
+  const uint32_t stage0 = bars + 128u;
   const int tid = threadIdx.x;
   const int y0 = blockIdx.y * kZsTY;
   const int x0 = blockIdx.x * kZsTX;
@@ -115,15 +119,15 @@ __global__ void __launch_bounds__(kZsThreads, 3)
   const int bx_hi = __double2int_rd(fmax(-big, fmin(big, cx_max))) + 2;
   const bool brick_ok = (by_hi - by0) < g.BY && (bx_hi - bx0) < g.BX;  // CTA-uniform
   if (!brick_ok) {
-    zsep_tile_from_global<T, ORDER, BOUNDARY, SCRUB>(p, y0, x0, zb, ze);
+    zsep_tile_from_global<T, ORDER, BOUNDARY, SCRUB, kZsTY>(p, y0, x0, zb, ze);
     return;
   }
 
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < kZsStages; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], kZsConsumers / 32);
+      mbar_init_u32(full0 + 8u * s, 1);
+      mbar_init_u32(empty0 + 8u * s, kZsConsumers / 32);
     }
     fence_mbar_init();
   }
@@ -152,10 +156,10 @@ __global__ void __launch_bounds__(kZsThreads, 3)
         const int s = h ? e.y : e.x;
         if (s > s_last) {
           const uint32_t stage = seq % kZsStages;
-          if (seq >= kZsStages) mbar_wait(&empty_bar[stage], ((seq / kZsStages) - 1) & 1);
+          if (seq >= kZsStages) mbar_wait_u32(empty0 + 8u * stage, ((seq / kZsStages) - 1) & 1);
           if (issuer) {
-            mbar_expect_tx(&full_bar[stage], static_cast<uint32_t>(g.BY) * g.BX * sizeof(T));
-            tma_load_3d(stage0 + stage * g.stage_bytes, &src_map, &full_bar[stage], bx0, by0, s);
+            mbar_expect_tx_u32(full0 + 8u * stage, static_cast<uint32_t>(g.BY) * g.BX * sizeof(T));
+            tma_load_3d_u32(stage0 + stage * g.stage_bytes, &src_map, full0 + 8u * stage, bx0, by0, s);
           }
           __syncwarp();
           s_last = s;
@@ -209,8 +213,6 @@ __global__ void __launch_bounds__(kZsThreads, 3)
   const int64_t plane_out = static_cast<int64_t>(p.oy) * p.dpitch;
   float* __restrict__ out_tile =
       p.dst + static_cast<int64_t>(zb) * plane_out + static_cast<int64_t>(y0) * p.dpitch + x0;
-  const uint32_t full0 = smem_u32(&full_bar[0]);
-  const uint32_t empty0 = smem_u32(&empty_bar[0]);
   const bool full_tile = (y0 + kZsTY <= p.oy) && (x0 + kZsTX <= p.ox);  // CTA-uniform
 
   // reduce the next plane of the producer's sequence to one value per point (p_last)
@@ -227,33 +229,41 @@ __global__ void __launch_bounds__(kZsThreads, 3)
         v[i] = ((inmask >> i) & 1u) ? t : 0.0f;
       }
     } else {
-      float t00[kZsPPT], t01[kZsPPT], t10[kZsPPT], t11[kZsPPT];
-#pragma unroll
-      for (int i = 0; i < kZsPPT; ++i) {
-        const uint32_t a0 = base + off[i];
-        const uint32_t a1 = a0 + pitch;
-        t00[i] = lds_elem<T>(a0);
-        t01[i] = lds_elem<T>(a0 + sizeof(T));
-        t10[i] = lds_elem<T>(a1);
-        t11[i] = lds_elem<T>(a1 + sizeof(T));
-      }
+      // groups of 4 points: 16 taps in flight, then 4 x (FMUL + 3 FFMA)
       bool bad = false;
 #pragma unroll
-      for (int i = 0; i < kZsPPT; ++i) {
-        v[i] = __fmaf_rn(w11[i], t11[i],
-                         __fmaf_rn(w10[i], t10[i], __fmaf_rn(w01[i], t01[i], __fmul_rn(w00[i], t00[i]))));
-        bad |= !(fabsf(v[i]) <= FLT_MAX);
+      for (int i0 = 0; i0 < kZsPPT; i0 += 4) {
+        float t00[4], t01[4], t10[4], t11[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t a0 = base + off[i0 + j];
+          const uint32_t a1 = a0 + pitch;
+          t00[j] = lds_elem<T>(a0);
+          t01[j] = lds_elem<T>(a0 + sizeof(T));
+          t10[j] = lds_elem<T>(a1);
+          t11[j] = lds_elem<T>(a1 + sizeof(T));
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int i = i0 + j;
+          v[i] = __fmaf_rn(w11[i], t11[j],
+                           __fmaf_rn(w10[i], t10[j], __fmaf_rn(w01[i], t01[j], __fmul_rn(w00[i], t00[j]))));
+          bad |= !(fabsf(v[i]) <= FLT_MAX);
+        }
       }
       if (sizeof(T) == 4 && bad) {
         // a NaN/inf tap was involved (possibly with zero weight): redo with the scrub
-        // (np.nan_to_num semantics); without SCRUB only the dummy taps of outside points are fixed
+        // (np.nan_to_num semantics), re-reading the taps; without SCRUB only the dummy taps of
+        // outside points are fixed
 #pragma unroll
         for (int i = 0; i < kZsPPT; ++i) {
           if (SCRUB) {
-            v[i] = __fmaf_rn(w11[i], scrub_value(t11[i]),
-                             __fmaf_rn(w10[i], scrub_value(t10[i]),
-                                       __fmaf_rn(w01[i], scrub_value(t01[i]),
-                                                 __fmul_rn(w00[i], scrub_value(t00[i])))));
+            const uint32_t a0 = base + off[i];
+            const uint32_t a1 = a0 + pitch;
+            v[i] = __fmaf_rn(w11[i], scrub_value(lds_elem<T>(a1 + sizeof(T))),
+                             __fmaf_rn(w10[i], scrub_value(lds_elem<T>(a1)),
+                                       __fmaf_rn(w01[i], scrub_value(lds_elem<T>(a0 + sizeof(T))),
+                                                 __fmul_rn(w00[i], scrub_value(lds_elem<T>(a0))))));
           } else if (!((inmask >> i) & 1u)) {
             v[i] = 0.0f;
           }
@@ -310,7 +320,7 @@ __global__ void __launch_bounds__(kZsThreads, 3)
 // host side
 // ---------------------------------------------------------------------------------------------
 template <typename T>
-static bool zsep_geometry(const AffineParams& p, ZsepGeom* g, size_t* smem_bytes) {
+static bool zsep_geometry(const AffineParams& p, int kZsTY, ZsepGeom* g, size_t* smem_bytes) {
   const double* m = p.m;
   if (m[1] != 0.0 || m[2] != 0.0 || m[4] != 0.0 || m[8] != 0.0) return false;
   if (!(m[0] > 0.0)) return false;
@@ -334,11 +344,11 @@ static bool zsep_geometry(const AffineParams& p, ZsepGeom* g, size_t* smem_bytes
   g->BY = BY;
   g->BX = BX;
   g->stage_bytes = stage;
-  *smem_bytes = static_cast<size_t>(stage) * kZsStages + 128;
+  *smem_bytes = static_cast<size_t>(stage) * kZsStages + 256;  // + barriers + alignment
   return true;
 }
 
-template <typename T, int ORDER, int BOUNDARY, bool SCRUB>
+template <typename T, int ORDER, int BOUNDARY, bool SCRUB, int kZsTY>
 static int launch_zsep(const AffineParams& p, ZsepGeom g, size_t smem_bytes, cudaStream_t stream) {
   EncodeTiledFn encode = get_encode_tiled();
   if (!encode) {
@@ -379,7 +389,7 @@ static int launch_zsep(const AffineParams& p, ZsepGeom g, size_t smem_bytes, cud
   if (tiles_y > 65535 || grid_z > 65535)
     return affine_gather_launch(p, sizeof(T) == 2 ? B2_DTYPE_U16 : B2_DTYPE_F32, stream);
 
-  auto kern = affine_zsep_kernel<T, ORDER, BOUNDARY, SCRUB>;
+  auto kern = affine_zsep_kernel<T, ORDER, BOUNDARY, SCRUB, kZsTY>;
   B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                static_cast<int>(smem_bytes)));
   const dim3 grid(tiles_x, tiles_y, grid_z);
@@ -403,23 +413,43 @@ static bool is_integer_translation(const AffineParams& p) {
   return true;
 }
 
-template <typename T>
-static int zsep_typed(const AffineParams& p, cudaStream_t stream, bool* eligible) {
+// Tile height: 32 rows (8 points per thread) amortise the per-plane barrier / bookkeeping
+// instructions over twice the points and shrink the in-plane halo; 16 rows keep 3 CTAs per SM.
+static int zsep_tile_rows() {
+  static const int ty = [] {
+    const char* e = getenv("B2_ZSEP_TY");
+    const int v = e ? atoi(e) : 0;
+    return (v == 16 || v == 32) ? v : 16;
+  }();
+  return ty;
+}
+
+template <typename T, int TY>
+static int zsep_typed_ty(const AffineParams& p, cudaStream_t stream, bool* eligible) {
   ZsepGeom g{};
   size_t smem = 0;
-  *eligible = zsep_geometry<T>(p, &g, &smem);
+  *eligible = zsep_geometry<T>(p, TY, &g, &smem);
   if (!*eligible) return B2_ERR_UNSUPPORTED;
   const bool scrub = p.scrub && sizeof(T) == 4;
   const int order = (p.order == 1 && is_integer_translation(p)) ? 0 : p.order;
-#define B2_ZS(ORD, BND)                                       \
-  (scrub ? launch_zsep<T, ORD, BND, true>(p, g, smem, stream) \
-         : launch_zsep<T, ORD, BND, false>(p, g, smem, stream))
+#define B2_ZS(ORD, BND)                                           \
+  (scrub ? launch_zsep<T, ORD, BND, true, TY>(p, g, smem, stream) \
+         : launch_zsep<T, ORD, BND, false, TY>(p, g, smem, stream))
   if (order == 0)
     return p.boundary == B2_BOUNDARY_CONSTANT ? B2_ZS(0, B2_BOUNDARY_CONSTANT)
                                               : B2_ZS(0, B2_BOUNDARY_ITK);
   return p.boundary == B2_BOUNDARY_CONSTANT ? B2_ZS(1, B2_BOUNDARY_CONSTANT)
                                             : B2_ZS(1, B2_BOUNDARY_ITK);
 #undef B2_ZS
+}
+
+template <typename T>
+static int zsep_typed(const AffineParams& p, cudaStream_t stream, bool* eligible) {
+  if (zsep_tile_rows() == 32) {
+    const int rc = zsep_typed_ty<T, 32>(p, stream, eligible);
+    if (*eligible) return rc;
+  }
+  return zsep_typed_ty<T, 16>(p, stream, eligible);
 }
 
 int affine_zsep_launch(const AffineParams& p, int src_dtype, cudaStream_t stream, bool* eligible) {
