@@ -49,6 +49,48 @@ __device__ __forceinline__ float brick_elem<uint16_t>(uint32_t addr) {
   return static_cast<float>(v);
 }
 
+// four taps of one source plane (rows a0 / a1, columns +0 / +1), loaded only when `need`;
+// otherwise the registers keep their value.  Predicated LDS: no branch, no wavefronts when off.
+template <typename T>
+__device__ __forceinline__ void brick_quad_if(bool need, uint32_t a0, uint32_t a1, float& v00,
+                                              float& v01, float& v10, float& v11);
+template <>
+__device__ __forceinline__ void brick_quad_if<float>(bool need, uint32_t a0, uint32_t a1, float& v00,
+                                                     float& v01, float& v10, float& v11) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.u32 p, %4, 0;\n"
+      "@p ld.shared.f32 %0, [%5];\n"
+      "@p ld.shared.f32 %1, [%5+4];\n"
+      "@p ld.shared.f32 %2, [%6];\n"
+      "@p ld.shared.f32 %3, [%6+4];\n"
+      "}\n"
+      : "+f"(v00), "+f"(v01), "+f"(v10), "+f"(v11)
+      : "r"(static_cast<uint32_t>(need)), "r"(a0), "r"(a1));
+}
+template <>
+__device__ __forceinline__ void brick_quad_if<uint16_t>(bool need, uint32_t a0, uint32_t a1,
+                                                        float& v00, float& v01, float& v10,
+                                                        float& v11) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b16 h0, h1, h2, h3;\n"
+      "setp.ne.u32 p, %4, 0;\n"
+      "@p ld.shared.u16 h0, [%5];\n"
+      "@p ld.shared.u16 h1, [%5+2];\n"
+      "@p ld.shared.u16 h2, [%6];\n"
+      "@p ld.shared.u16 h3, [%6+2];\n"
+      "@p cvt.rn.f32.u16 %0, h0;\n"
+      "@p cvt.rn.f32.u16 %1, h1;\n"
+      "@p cvt.rn.f32.u16 %2, h2;\n"
+      "@p cvt.rn.f32.u16 %3, h3;\n"
+      "}\n"
+      : "+f"(v00), "+f"(v01), "+f"(v10), "+f"(v11)
+      : "r"(static_cast<uint32_t>(need)), "r"(a0), "r"(a1));
+}
+
 __device__ __forceinline__ double coord_full(const double* m, double zf, double yf, double xf) {
   return __dadd_rn(__dadd_rn(__dadd_rn(m[3], __dmul_rn(zf, m[0])), __dmul_rn(yf, m[1])),
                    __dmul_rn(xf, m[2]));
@@ -79,8 +121,91 @@ __device__ __noinline__ float brick_sample_exact(const AffineParams& p, uint32_t
   return lerp_w(p0, p1, tz.w);
 }
 
+struct BrickCol {
+  uint32_t brick, plane_b, row_b;
+  int64_t out_plane;
+  float u0z, u0y, u0x;  // brick-local coordinate of the column's first voxel
+  float mz, my, mx;     // coordinate step per output plane (first column of the matrix)
+};
+
+// One (y, x) column of a full-depth tile, order 1.  The voxels are walked along output z; every
+// strictly interior voxel (both taps valid on every axis, kEdge away from every decision edge) is
+// interpolated from the brick in fp32 and stored.  Returns the bit mask of the voxels that were NOT
+// written (not strictly interior, or a non-finite tap turned up): the caller finishes those on the
+// exact path.  CHECK = false: the whole tile is known to be strictly interior (decided once per
+// CTA from the brick hull) and the per-voxel test is compiled out.  ~40 instructions per voxel.
+template <typename T, bool SCRUB, bool CHECK>
+__device__ __forceinline__ uint32_t brick_column_linear(const BrickCol& c, const float (&mid)[3],
+                                                        const float (&half)[3],
+                                                        float* __restrict__ out) {
+  constexpr uint32_t es = static_cast<uint32_t>(sizeof(T));
+  // floor via the magic constant in round-down mode: t = RD(u + kMagic) holds floor(u) in its low
+  // mantissa bits (FADD.RM is a full-rate FADD), weight w = u - (t - kMagic).  The sum of the
+  // three index biases (0x4B400000 each) is folded into the base address.
+  const uint32_t abase = c.brick - 0x4B400000u * (c.plane_b + c.row_b + es);
+  uint32_t rest = 0;
+  // taps of the upper source plane (iz+1) of the previous voxel: when the next voxel of the column
+  // sits in the same (y, x) cell one plane further - the usual case for m00 ~ 1 and small
+  // out-of-plane terms - they are its lower-plane taps and are not read again (halves the
+  // shared-memory wavefronts)
+  float r0 = 0.0f, r1 = 0.0f, r2 = 0.0f, r3 = 0.0f;
+  uint32_t a_up = 0xffffffffu;
+  float* __restrict__ o = out;
+#pragma unroll
+  for (int k = 0; k < kBrTZ; ++k, o += c.out_plane) {
+    const float kf = static_cast<float>(k);
+    const float uz = __fmaf_rn(kf, c.mz, c.u0z);
+    const float uy = __fmaf_rn(kf, c.my, c.u0y);
+    const float ux = __fmaf_rn(kf, c.mx, c.u0x);
+    if (CHECK) {
+      const bool interior = fabsf(uz - mid[0]) <= half[0] - kEdge &&
+                            fabsf(uy - mid[1]) <= half[1] - kEdge &&
+                            fabsf(ux - mid[2]) <= half[2] - kEdge;
+      if (!interior) {
+        rest |= 1u << k;
+        a_up = 0xffffffffu;
+        continue;
+      }
+    }
+    const float tz = __fadd_rd(uz, kMagic), ty = __fadd_rd(uy, kMagic), tx = __fadd_rd(ux, kMagic);
+    const float wz = uz - (tz - kMagic);
+    const float wy = uy - (ty - kMagic);
+    const float wx = ux - (tx - kMagic);
+    const uint32_t a00 = static_cast<uint32_t>(__float_as_int(tz)) * c.plane_b +
+                         (static_cast<uint32_t>(__float_as_int(ty)) * c.row_b +
+                          (static_cast<uint32_t>(__float_as_int(tx)) * es + abase));
+    const uint32_t a10 = a00 + c.plane_b;
+    // lower plane: r0..r3 keep their value unless the cell changed
+    brick_quad_if<T>(a00 != a_up, a00, a00 + c.row_b, r0, r1, r2, r3);
+    const float v000 = r0, v001 = r1, v010 = r2, v011 = r3;
+    r0 = brick_elem<T>(a10);
+    r1 = brick_elem<T>(a10 + es);
+    r2 = brick_elem<T>(a10 + c.row_b);
+    r3 = brick_elem<T>(a10 + c.row_b + es);
+    a_up = a10;
+    float v;
+    if (SCRUB || sizeof(T) == 2) {
+      // finite taps (uint16, or verified below): v0 + w * (v1 - v0), 2 instructions per lerp
+      const float q00 = __fmaf_rn(wx, v001 - v000, v000), q01 = __fmaf_rn(wx, v011 - v010, v010);
+      const float q10 = __fmaf_rn(wx, r1 - r0, r0), q11 = __fmaf_rn(wx, r3 - r2, r2);
+      const float q0 = __fmaf_rn(wy, q01 - q00, q00), q1 = __fmaf_rn(wy, q11 - q10, q10);
+      v = __fmaf_rn(wz, q1 - q0, q0);
+      // a NaN/inf tap makes v non-finite: the exact path applies the scrub per tap
+      if (sizeof(T) == 4 && !(fabsf(v) <= FLT_MAX)) {
+        rest |= 1u << k;
+        continue;
+      }
+    } else {
+      v = lerp_w(lerp_w(lerp_w(v000, v001, wx), lerp_w(v010, v011, wx), wy),
+                 lerp_w(lerp_w(r0, r1, wx), lerp_w(r2, r3, wx), wy), wz);
+    }
+    st_global_cs(o, v);
+  }
+  return rest;
+}
+
 template <typename T, int ORDER, int BOUNDARY, bool SCRUB>
-__global__ void __launch_bounds__(kBrThreads, 3)
+__global__ void __launch_bounds__(kBrThreads, 4)
     affine_brick_kernel(const __grid_constant__ CUtensorMap src_map,
                         const __grid_constant__ AffineParams p,
                         const __grid_constant__ BrickGeom g, const int tiles_z, const int tiles_x) {
@@ -97,23 +222,64 @@ __global__ void __launch_bounds__(kBrThreads, 3)
   const int nz = min(kBrTZ, p.oz - z0);
 
   // ---- brick origin: exact float64 coordinate of the tile origin + the host-computed hull of a
-  //      full tile (CTA-uniform; the 1e-6 guards absorb the rounding of the hull sums; the host
-  //      guarantees |coordinate| < 1e9 over the whole output so the int conversions are defined)
-  int b0[3], bhi[3];
-  float c0l[3];  // tile-origin coordinate relative to the brick origin
-  {
+  //      full tile (the 1e-6 guards absorb the rounding of the hull sums; the host guarantees
+  //      |coordinate| < 1e9 over the whole output so the int conversions are defined).
+  //      CTA-uniform, so ONE thread evaluates it (float64, ~170 instructions), issues the TMA
+  //      load and publishes the result through shared memory.
+  // b0[3], bits(c0l[3]), flags (1 = brick ok, 2 = tile strictly interior, 4 = tile outside)
+  __shared__ int s_geo[8];
+  if (threadIdx.x == 0) {
+    int tb0[3], tbhi[3];
     const double zf = static_cast<double>(z0 + p.cz), yf = static_cast<double>(y0 + p.cy),
                  xf = static_cast<double>(x0 + p.cx);
+    const int n[3] = {p.sz, p.sy, p.sx};
+    bool inside = true, outside = false;
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
       const double c = coord_full(p.m + 4 * d, zf, yf, xf);
-      b0[d] = __double2int_rd(c + (g.neg[d] - 1e-6));
-      if (d == 2) b0[d] &= ~(kVec - 1);  // innermost TMA coordinate must be 16-byte aligned
-      bhi[d] = __double2int_rd(c + (g.pos[d] + 1e-6)) + 2;
-      c0l[d] = static_cast<float>(c - static_cast<double>(b0[d]));
+      tb0[d] = __double2int_rd(c + (g.neg[d] - 1e-6));
+      // the hull of the tile misses the source (and its half-voxel ITK band) on this axis
+      outside = outside || tb0[d] >= n[d] + 1 || __double2int_rd(c + (g.pos[d] + 1e-6)) <= -2;
+      // every tap of every voxel of a full tile is a valid source index, with >= 1 voxel margin
+      inside = inside && tb0[d] >= 1;
+      if (d == 2) tb0[d] &= ~(kVec - 1);  // innermost TMA coordinate must be 16-byte aligned
+      tbhi[d] = __double2int_rd(c + (g.pos[d] + 1e-6)) + 2;
+      inside = inside && tbhi[d] <= n[d] - 1;
+      s_geo[d] = tb0[d];
+      s_geo[3 + d] = __float_as_int(static_cast<float>(c - static_cast<double>(tb0[d])));
+    }
+    const bool ok = (tbhi[0] - tb0[0]) < g.BZ && (tbhi[1] - tb0[1]) < g.BY && (tbhi[2] - tb0[2]) < g.BX;
+    s_geo[6] = (ok ? 1 : 0) | (inside ? 2 : 0) | (outside ? 4 : 0);
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+    if (ok && !outside) {
+      mbar_expect_tx(&bar, static_cast<uint32_t>(g.bytes));
+      tma_load_3d(brick, &src_map, &bar, tb0[2], tb0[1], tb0[0]);
     }
   }
-  const bool brick_ok = (bhi[0] - b0[0]) < g.BZ && (bhi[1] - b0[1]) < g.BY && (bhi[2] - b0[2]) < g.BX;
+  __syncthreads();
+  int b0[3];
+  float c0l[3];  // tile-origin coordinate relative to the brick origin
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    b0[d] = s_geo[d];
+    c0l[d] = __int_as_float(s_geo[3 + d]);
+  }
+  const bool brick_ok = (s_geo[6] & 1) != 0;
+  const bool tile_in = (s_geo[6] & 2) != 0;
+  if (s_geo[6] & 4) {  // the whole tile maps outside the source: zeros, nothing to load
+    const int lx_ = threadIdx.x % kBrTX, ly_ = threadIdx.x / kBrTX;
+    if (x0 + lx_ < p.ox) {
+#pragma unroll
+      for (int c = 0; c < kBrCols; ++c) {
+        const int y = y0 + ly_ + c * kBrRowStep;
+        if (y >= p.oy) continue;
+        float* o = p.dst + (static_cast<int64_t>(z0) * p.oy + y) * p.dpitch + (x0 + lx_);
+        for (int k = 0; k < nz; ++k, o += static_cast<int64_t>(p.oy) * p.dpitch) st_global_cs(o, 0.0f);
+      }
+    }
+    return;
+  }
 
   const int lx = threadIdx.x % kBrTX, ly = threadIdx.x / kBrTX;
   const int x = x0 + lx;
@@ -128,16 +294,6 @@ __global__ void __launch_bounds__(kBrThreads, 3)
               affine_sample_generic<T, ORDER, BOUNDARY, SCRUB>(p, z0 + k, y, x);
     }
     return;
-  }
-
-  if (threadIdx.x == 0) {
-    mbar_init(&bar, 1);
-    fence_mbar_init();
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    mbar_expect_tx(&bar, static_cast<uint32_t>(g.bytes));
-    tma_load_3d(brick, &src_map, &bar, b0[2], b0[1], b0[0]);
   }
 
   // ---- per-axis constants in brick-local coordinates
@@ -177,68 +333,31 @@ __global__ void __launch_bounds__(kBrThreads, 3)
     float* __restrict__ o = out;
 
     if (ORDER == 1 && nz == kBrTZ) {
-      // ---- whole-column fast path: the coordinate is linear in k, so a column whose two end
-      // voxels are strictly interior is strictly interior throughout (the box is convex) and needs
-      // no per-voxel edge tests.  ~48 instructions per voxel instead of ~96.
-      const float kl = static_cast<float>(kBrTZ - 1);
-      bool col_in = true;
-#pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        col_in = col_in && fabsf(u0[d] - mid[d]) <= half[d] - kEdge &&
-                 fabsf(__fmaf_rn(kl, mcol[d][0], u0[d]) - mid[d]) <= half[d] - kEdge;
+      // ---- column fast path (order 1, full-depth tile): see brick_column_linear
+      const BrickCol cc{brick, plane_b, row_b, out_plane, u0[0], u0[1], u0[2], mcol[0][0], mcol[1][0],
+                        mcol[2][0]};
+      uint32_t rest;
+      if (tile_in) {
+        rest = brick_column_linear<T, SCRUB, false>(cc, mid, half, out);
+      } else {
+        rest = brick_column_linear<T, SCRUB, true>(cc, mid, half, out);
       }
-      if (col_in) {
-        // floor via the magic constant in round-down mode: t = RD(u + kMagic) holds floor(u) in its
-        // low mantissa bits (FADD.RM is a full-rate FADD), weight w = u - (t - kMagic)
-        // sum of the three index biases (0x4B400000 each) folded into the base address
-        const uint32_t abase = brick - 0x4B400000u * (plane_b + row_b + es);
-        float vout[kBrTZ];
-        uint32_t bad = 0;
-#pragma unroll
-        for (int k = 0; k < kBrTZ; ++k) {
-          const float kf = static_cast<float>(k);
-          const float uz = __fmaf_rn(kf, mcol[0][0], u0[0]);
-          const float uy = __fmaf_rn(kf, mcol[1][0], u0[1]);
-          const float ux = __fmaf_rn(kf, mcol[2][0], u0[2]);
-          const float tz = __fadd_rd(uz, kMagic), ty = __fadd_rd(uy, kMagic), tx = __fadd_rd(ux, kMagic);
-          const float wz = uz - (tz - kMagic);
-          const float wy = uy - (ty - kMagic);
-          const float wx = ux - (tx - kMagic);
-          const uint32_t a00 = static_cast<uint32_t>(__float_as_int(tz)) * plane_b +
-                               (static_cast<uint32_t>(__float_as_int(ty)) * row_b +
-                                (static_cast<uint32_t>(__float_as_int(tx)) * es + abase));
-          const uint32_t a01 = a00 + row_b, a10 = a00 + plane_b, a11 = a10 + row_b;
-          const float v000 = brick_elem<T>(a00), v001 = brick_elem<T>(a00 + es);
-          const float v010 = brick_elem<T>(a01), v011 = brick_elem<T>(a01 + es);
-          const float v100 = brick_elem<T>(a10), v101 = brick_elem<T>(a10 + es);
-          const float v110 = brick_elem<T>(a11), v111 = brick_elem<T>(a11 + es);
-          float v;
-          if (SCRUB || sizeof(T) == 2) {
-            // finite taps (uint16, or verified below): v0 + w * (v1 - v0), 2 instructions per lerp
-            const float r00 = __fmaf_rn(wx, v001 - v000, v000), r01 = __fmaf_rn(wx, v011 - v010, v010);
-            const float r10 = __fmaf_rn(wx, v101 - v100, v100), r11 = __fmaf_rn(wx, v111 - v110, v110);
-            const float q0 = __fmaf_rn(wy, r01 - r00, r00), q1 = __fmaf_rn(wy, r11 - r10, r10);
-            v = __fmaf_rn(wz, q1 - q0, q0);
-            // a NaN/inf tap makes v non-finite: the exact path applies the scrub per tap
-            if (sizeof(T) == 4 && !(fabsf(v) <= FLT_MAX)) bad |= 1u << k;
-          } else {
-            v = lerp_w(lerp_w(lerp_w(v000, v001, wx), lerp_w(v010, v011, wx), wy),
-                       lerp_w(lerp_w(v100, v101, wx), lerp_w(v110, v111, wx), wy), wz);
-          }
-          vout[k] = v;
-        }
-#pragma unroll
-        for (int k = 0; k < kBrTZ; ++k, o += out_plane)
-          if (!((bad >> k) & 1u)) st_global_cs(o, vout[k]);
-        while (bad) {
-          const int k = __ffs(bad) - 1;
-          bad &= bad - 1;
-          st_global_cs(out + k * out_plane,
-                       brick_sample_exact<T, ORDER, BOUNDARY, SCRUB>(p, brick, b0[0], b0[1], b0[2],
-                                                                     g.BY, g.BX, z0 + k, y, x));
-        }
-        continue;
+      // voxels near a decision edge, outside the source, or with non-finite taps: exact path
+      while (rest) {
+        const int k = __ffs(rest) - 1;
+        rest &= rest - 1;
+        const float kf = static_cast<float>(k);
+        const float dz = fabsf(__fmaf_rn(kf, mcol[0][0], u0[0]) - mid[0]);
+        const float dy = fabsf(__fmaf_rn(kf, mcol[1][0], u0[1]) - mid[1]);
+        const float dx = fabsf(__fmaf_rn(kf, mcol[2][0], u0[2]) - mid[2]);
+        const bool outside = dz > half[0] + 0.5f + kEdge || dy > half[1] + 0.5f + kEdge ||
+                             dx > half[2] + 0.5f + kEdge;
+        const float v = outside ? 0.0f
+                                : brick_sample_exact<T, ORDER, BOUNDARY, SCRUB>(
+                                      p, brick, b0[0], b0[1], b0[2], g.BY, g.BX, z0 + k, y, x);
+        st_global_cs(out + k * out_plane, v);
       }
+      continue;
     }
 #pragma unroll 2
     for (int k = 0; k < nz; ++k, o += out_plane) {
