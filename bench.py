@@ -355,7 +355,10 @@ def run_b200(args, w, rank, world, local_rank):
     pageable_value = None
     if e2e_units and rank == 0 and world == 1 and w["kind"] in ("deskew", "register", "stabilize"):
         src_pg = np.array(h_in[0], copy=True)
-        for rep in range(2):
+        res = None
+        best_pg = None
+        for rep in range(5):  # the first two calls grow the pinned result pool; steady state after
+            res = None        # drop the previous result, as process_single_position does
             t0 = time.perf_counter()
             if w["kind"] == "deskew":
                 res = b2._fast_deskew_czyx(src_pg[None], device=f"cuda:{local_rank}",
@@ -367,7 +370,9 @@ def run_b200(args, w, rank, world, local_rank):
                 res = b2.affine_warp(src_pg, mats[0], out_shape, order=1, boundary="itk",
                                      device=local_rank)
             dt_pg = time.perf_counter() - t0
-        pageable_value = out_vox / dt_pg / 1e9
+            if rep >= 2:
+                best_pg = dt_pg if best_pg is None else min(best_pg, dt_pg)
+        pageable_value = out_vox / best_pg / 1e9
         del res, src_pg
 
     peak, peak_src = read_peaks()
@@ -403,7 +408,7 @@ def run_b200(args, w, rank, world, local_rank):
                      # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the
                      # committed ncu --set full capture of this workload (profiles/r1_*.txt)
                      "traffic": w.get("ncu_traffic"),
-                     "kernel": {"deskew": "deskew_tma_kernel", "chain": "deskew_tma_kernel + affine_zsep_kernel (bytes and time of both)"}.get(w["kind"], "affine_gather_kernel" if w.get("generic") else "affine_zsep_kernel"),
+                     "kernel": {"deskew": "deskew_tma_kernel", "chain": "deskew_tma_kernel + affine_zsep_kernel (bytes and time of both)"}.get(w["kind"], "affine_brick_kernel" if w.get("generic") else "affine_zsep_kernel"),
                      "algorithmic_bytes_per_launch": int(bytes_unit),
                      "launch_ms": round(launch_ms, 4), "peak_source": peak_src},
     }

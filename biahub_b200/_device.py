@@ -143,9 +143,109 @@ def pinned_empty(shape, dtype):
     return buf.numpy()[:n].view(dtype).reshape(shape)
 
 
+class _PinnedHolder:
+    """Owner object of one result array: numpy keeps it as ``.base`` of the array and of every
+    view of it, so the block returns to the pool when the last of them is garbage-collected."""
+
+    __slots__ = ("block", "__array_interface__", "__weakref__")
+
+    def __init__(self, block, shape, dtype):
+        self.block = block
+        self.__array_interface__ = {
+            "shape": tuple(int(v) for v in shape),
+            "typestr": np.dtype(dtype).str,
+            "data": (block["ptr"], False),
+            "version": 3,
+        }
+
+
+class PinnedResultPool:
+    """Recycling pool of page-locked blocks for RESULT arrays.
+
+    The reference's callers (``process_single_position``) take a fresh array per (t, c) unit, write
+    it to zarr and drop it.  A fresh pageable ``np.empty`` costs a staging copy out of the pinned
+    ring plus the first-touch page faults of 1.5 GB per mantis volume — 2-3x the PCIe time.  Blocks
+    from this pool are the DMA target themselves; a block is handed out again once the array (and
+    all its views) is gone.  Bounded by ``BIAHUB_B200_PINNED_POOL_MB`` (default 6144; 0 disables):
+    beyond that, results fall back to ordinary pageable arrays.
+    """
+
+    def __init__(self, alloc=None, cap_bytes=None):
+        self._alloc = alloc or self._alloc_pinned
+        if cap_bytes is None:
+            cap_bytes = int(os.environ.get("BIAHUB_B200_PINNED_POOL_MB", "6144")) << 20
+        self.cap_bytes = cap_bytes
+        self.free = []          # blocks: {"ptr": int, "nbytes": int, "keep": object}
+        self.total_bytes = 0
+        self.handed_out = 0
+        import threading
+
+        self._lock = threading.Lock()
+
+    @staticmethod
+    def _alloc_pinned(nbytes):
+        import torch
+
+        t = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+        return {"ptr": t.data_ptr(), "nbytes": nbytes, "keep": t}
+
+    def _release(self, block):
+        with self._lock:
+            self.handed_out -= 1
+            self.free.append(block)
+
+    def empty(self, shape, dtype=np.float32):
+        """A writeable C-contiguous array of ``shape`` in pinned memory, or None when the pool is
+        disabled / exhausted."""
+        import weakref
+
+        dtype = np.dtype(dtype)
+        need = max(int(np.prod(shape)) * dtype.itemsize, 1)
+        block = None
+        with self._lock:
+            fits = [b for b in self.free if b["nbytes"] >= need]
+            if fits:
+                block = min(fits, key=lambda b: b["nbytes"])
+                self.free.remove(block)
+            elif self.total_bytes + need > self.cap_bytes:
+                # make room by dropping idle blocks that are too small before giving up
+                while self.free and self.total_bytes + need > self.cap_bytes:
+                    self.total_bytes -= self.free.pop(0)["nbytes"]
+                if self.total_bytes + need > self.cap_bytes:
+                    return None
+        if block is None:
+            try:
+                block = self._alloc(need)
+            except Exception:  # noqa: BLE001 - no driver / pinned memory exhausted: pageable result
+                return None
+            with self._lock:
+                self.total_bytes += block["nbytes"]
+        holder = _PinnedHolder(block, shape, dtype)
+        arr = np.asarray(holder)
+        with self._lock:
+            self.handed_out += 1
+        weakref.finalize(holder, self._release, block)
+        return arr
+
+
+_result_pool = None
+
+
+def result_pool() -> PinnedResultPool:
+    global _result_pool
+    if _result_pool is None:
+        _result_pool = PinnedResultPool()
+    return _result_pool
+
+
 def check_out(out, shape):
+    """The result buffer: the caller's ``out`` (validated) or a fresh array — from the pinned
+    result pool when possible, else an ordinary ``np.empty``."""
     if out is None:
-        return np.empty(shape, dtype=np.float32)
+        arr = None
+        if int(np.prod(shape)) >= (1 << 20):  # small results are not worth a pinned block
+            arr = result_pool().empty(shape, np.float32)
+        return arr if arr is not None else np.empty(shape, dtype=np.float32)
     if not (isinstance(out, np.ndarray) and out.dtype == np.float32 and out.shape == tuple(shape)
             and out.flags.c_contiguous):
         raise ValueError(f"out must be a C-contiguous float32 array of shape {tuple(shape)}")

@@ -19,6 +19,9 @@
 namespace b2 {
 
 // tile height kZsTY is a template parameter (16 or 32 rows -> 4 or 8 output points per thread)
+#ifndef B2_ZSEP_MAXREG
+#define B2_ZSEP_MAXREG 72  // 3 CTAs (27 warps) per SM
+#endif
 constexpr int kZsTX = 64;
 constexpr int kZsConsumers = 256;
 constexpr int kZsThreads = kZsConsumers + 32;  // + one producer warp
@@ -69,7 +72,7 @@ __device__ __noinline__ void zsep_tile_from_global(const AffineParams& p, int y0
 }
 
 template <typename T, int ORDER, int BOUNDARY, bool SCRUB, int kZsTY>
-__global__ void __launch_bounds__(kZsThreads) __maxnreg__(kZsTY == 16 ? 72 : 112)
+__global__ void __launch_bounds__(kZsThreads) __maxnreg__(kZsTY == 16 ? B2_ZSEP_MAXREG : 112)
     affine_zsep_kernel(const __grid_constant__ CUtensorMap src_map,
                        const __grid_constant__ AffineParams p, const ZsepGeom g) {
   constexpr int kZsPPT = (kZsTY * kZsTX) / kZsConsumers;  // output points per consumer thread

@@ -181,3 +181,45 @@ def test_largest_interior_rectangle_bruteforce():
                             best = max(best, (y1 - y0) * (x1 - x0))
         assert w * h == best
     assert largest_interior_rectangle(np.zeros((3, 3), bool)) == (0, 0, 0, 0)
+
+
+def test_pinned_result_pool_recycles_blocks():
+    """Result arrays come from a recycling pool: a block is reused once the array AND its views
+    are gone, the cap is honoured, and the arrays behave like fresh C-contiguous float32 arrays."""
+    import gc
+
+    from biahub_b200._device import PinnedResultPool
+
+    allocs = []
+
+    def fake_alloc(nbytes):
+        buf = np.empty(nbytes, dtype=np.uint8)
+        allocs.append(nbytes)
+        return {"ptr": buf.ctypes.data, "nbytes": nbytes, "keep": buf}
+
+    pool = PinnedResultPool(alloc=fake_alloc, cap_bytes=3 * 4 * 1000)
+    a = pool.empty((10, 10, 10), np.float32)
+    assert a.shape == (10, 10, 10) and a.dtype == np.float32
+    assert a.flags.c_contiguous and a.flags.writeable
+    a[...] = 7.0
+    ptr_a = a.ctypes.data
+    view = a[2:5]
+    del a
+    gc.collect()
+    assert pool.handed_out == 1 and not pool.free          # the view keeps the block alive
+    b = pool.empty((10, 10, 10), np.float32)               # second block
+    assert b.ctypes.data != ptr_a and len(allocs) == 2
+    del view
+    gc.collect()
+    assert len(pool.free) == 1
+    c = pool.empty((5, 10, 10), np.float32)                # smaller request reuses the idle block
+    assert c.ctypes.data == ptr_a and len(allocs) == 2
+    d = pool.empty((10, 10, 10), np.float32)               # third block: at the cap now
+    assert d is not None and len(allocs) == 3
+    assert pool.empty((10, 10, 10), np.float32) is None    # exhausted -> caller falls back
+    del b, c, d
+    gc.collect()
+    assert pool.handed_out == 0 and len(pool.free) == 3
+    # a request larger than any idle block evicts idle blocks to stay under the cap
+    e = pool.empty((20, 10, 10), np.float32)
+    assert e is not None and pool.total_bytes <= pool.cap_bytes
