@@ -509,6 +509,8 @@ static int launch_brick(const AffineParams& p, const BrickGeom& g, size_t smem_b
   auto kern = affine_brick_kernel<T, ORDER, BOUNDARY, SCRUB>;
   B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                static_cast<int>(smem_bytes)));
+  B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                               cudaSharedmemCarveoutMaxShared));
   kern<<<static_cast<unsigned>(tiles), kBrThreads, smem_bytes, stream>>>(map, p, g, tiles_z, tiles_x);
   B2_CUDA(cudaGetLastError());
   count_launch();

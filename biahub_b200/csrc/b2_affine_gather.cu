@@ -1,6 +1,8 @@
 // Generic affine pull warp: one thread per output voxel, float64 coordinates in the oracle's op
 // order, taps fetched with LDG through L1/L2.  Correct for ANY 3x4 matrix, shape and alignment;
 // it is the fallback of the TMA-staged kernels (b2_affine_zsep.cu), not a CPU fallback.
+#include <cstdlib>
+
 #include "b2_affine.cuh"
 
 namespace b2 {
@@ -120,7 +122,13 @@ int affine_device(const void* src, int src_dtype, int64_t sz, int64_t sy, int64_
     bool eligible = false;
     int rc = affine_zsep_launch(p, src_dtype, stream, &eligible);
     if (eligible) return rc;
-    rc = affine_brick_launch(p, src_dtype, stream, &eligible);  // generic matrices
+    // generic matrices: z-marching plane ring (order 1, m00 > 0), else one 3-D brick per tile
+    const char* no_march = getenv("B2_AFFINE_NO_MARCH");  // A/B switch for tests and sweeps
+    if (!(no_march && no_march[0] == '1')) {
+      rc = affine_march_launch(p, src_dtype, stream, &eligible);
+      if (eligible) return rc;
+    }
+    rc = affine_brick_launch(p, src_dtype, stream, &eligible);
     if (eligible) return rc;
     if (path == B2_PATH_TMA) {
       set_error("affine3d: TMA paths not eligible (need 16-byte aligned source rows and a "
