@@ -140,6 +140,5 @@ int affine_gather_launch(const AffineParams& p, int src_dtype, cudaStream_t stre
 // returns B2_ERR_UNSUPPORTED (without setting an error) when the matrix/shape is not eligible
 int affine_zsep_launch(const AffineParams& p, int src_dtype, cudaStream_t stream, bool* eligible);
 int affine_brick_launch(const AffineParams& p, int src_dtype, cudaStream_t stream, bool* eligible);
-int affine_march_launch(const AffineParams& p, int src_dtype, cudaStream_t stream, bool* eligible);
 
 }  // namespace b2

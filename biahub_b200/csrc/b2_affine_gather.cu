@@ -122,13 +122,7 @@ int affine_device(const void* src, int src_dtype, int64_t sz, int64_t sy, int64_
     bool eligible = false;
     int rc = affine_zsep_launch(p, src_dtype, stream, &eligible);
     if (eligible) return rc;
-    // generic matrices: z-marching plane ring (order 1, m00 > 0), else one 3-D brick per tile
-    const char* no_march = getenv("B2_AFFINE_NO_MARCH");  // A/B switch for tests and sweeps
-    if (!(no_march && no_march[0] == '1')) {
-      rc = affine_march_launch(p, src_dtype, stream, &eligible);
-      if (eligible) return rc;
-    }
-    rc = affine_brick_launch(p, src_dtype, stream, &eligible);
+    rc = affine_brick_launch(p, src_dtype, stream, &eligible);  // generic matrices
     if (eligible) return rc;
     if (path == B2_PATH_TMA) {
       set_error("affine3d: TMA paths not eligible (need 16-byte aligned source rows and a "
