@@ -6,6 +6,7 @@ Drop-in replacements (same names/signatures as the reference) for the array-comp
     biahub_b200.deskew     ↔ reference biahub/deskew.py:43-579
     biahub_b200.register   ↔ reference biahub/register.py:32-281, 397-398
     biahub_b200.stabilize  ↔ reference biahub/stabilize.py:32-90
+    biahub_b200.flat_field ↔ reference biahub/flat_field.py:105-166 (the stage before deskew)
 
 All arithmetic runs in ``_lib/libbiahub_b200.so`` (hand-written CUDA, C ABI in
 ``include/biahub_b200.h``); there is no CPU or PyTorch fallback.  ``patch.install()`` re-points
@@ -35,6 +36,7 @@ from .register import (  # noqa: F401
     get_3D_rotation_matrix,
     rescale_voxel_size,
 )
+from .flat_field import _flat_field_czyx, flat_field_correction, flat_field_zyx  # noqa: F401
 from .pipeline import deskew_then_register  # noqa: F401
 from .stabilize import apply_stabilization_transform  # noqa: F401
 

@@ -238,17 +238,18 @@ def result_pool() -> PinnedResultPool:
     return _result_pool
 
 
-def check_out(out, shape):
+def check_out(out, shape, dtype=np.float32):
     """The result buffer: the caller's ``out`` (validated) or a fresh array — from the pinned
     result pool when possible, else an ordinary ``np.empty``."""
+    dtype = np.dtype(dtype)
     if out is None:
         arr = None
         if int(np.prod(shape)) >= (1 << 20):  # small results are not worth a pinned block
-            arr = result_pool().empty(shape, np.float32)
-        return arr if arr is not None else np.empty(shape, dtype=np.float32)
-    if not (isinstance(out, np.ndarray) and out.dtype == np.float32 and out.shape == tuple(shape)
+            arr = result_pool().empty(shape, dtype)
+        return arr if arr is not None else np.empty(shape, dtype=dtype)
+    if not (isinstance(out, np.ndarray) and out.dtype == dtype and out.shape == tuple(shape)
             and out.flags.c_contiguous):
-        raise ValueError(f"out must be a C-contiguous float32 array of shape {tuple(shape)}")
+        raise ValueError(f"out must be a C-contiguous {dtype} array of shape {tuple(shape)}")
     return out
 
 

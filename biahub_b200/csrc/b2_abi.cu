@@ -71,6 +71,14 @@ int host_affine(const void* h_src, int src_dtype, int64_t sz, int64_t sy, int64_
                 int64_t oz, int64_t oy, int64_t ox, const double* M12, const int64_t* crop_start,
                 int order, int boundary, int scrub, int device);
 int host_release();
+size_t flatfield_workspace_bytes(int64_t Y, int64_t X);
+int flatfield_begin(int64_t Y, int64_t X, void* ws, cudaStream_t stream);
+int flatfield_median(const void* src, int64_t Z, int64_t Y, int64_t X, void* ws, size_t ws_bytes,
+                     int64_t p0, int64_t pn, cudaStream_t stream);
+int flatfield_apply(const void* src, int64_t Z, int64_t Y, int64_t X, void* dst, int dst_dtype,
+                    void* ws, size_t ws_bytes, int64_t z0, int64_t zn, cudaStream_t stream);
+int host_flatfield(const void* h_src, int64_t Z, int64_t Y, int64_t X, void* h_dst, int dst_dtype,
+                   int device);
 
 static int require_device() {
   int n = 0;
@@ -185,6 +193,27 @@ int b2h_affine3d(const void* h_src, int src_dtype, int64_t sz, int64_t sy, int64
   if (rc) return rc;
   return b2::host_affine(h_src, src_dtype, sz, sy, sx, h_dst, oz, oy, ox, M12, crop_start, order,
                          boundary, scrub_nonfinite, device);
+}
+
+size_t b2_flatfield_workspace(int64_t y, int64_t x) { return b2::flatfield_workspace_bytes(y, x); }
+
+int b2_flatfield_u16(const void* src, int64_t z, int64_t y, int64_t x, void* dst, int dst_dtype,
+                     void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = b2::require_device();
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // argument checks happen in the first step; the accumulator is cleared only once they passed
+  if ((rc = b2::flatfield_median(src, z, y, x, workspace, workspace_bytes, 0, 0, st))) return rc;
+  if ((rc = b2::flatfield_begin(y, x, workspace, st))) return rc;
+  if ((rc = b2::flatfield_median(src, z, y, x, workspace, workspace_bytes, 0, y * x, st))) return rc;
+  return b2::flatfield_apply(src, z, y, x, dst, dst_dtype, workspace, workspace_bytes, 0, z, st);
+}
+
+int b2h_flatfield_u16(const void* h_src, int64_t z, int64_t y, int64_t x, void* h_dst, int dst_dtype,
+                      int device) {
+  int rc = b2::require_device();
+  if (rc) return rc;
+  return b2::host_flatfield(h_src, z, y, x, h_dst, dst_dtype, device);
 }
 
 int b2h_release(void) { return b2::host_release(); }

@@ -35,6 +35,13 @@ int affine_device(const void* src, int src_dtype, int64_t sz, int64_t sy, int64_
                   int order, int boundary, int scrub, int path, cudaStream_t stream,
                   int64_t src_row_pitch, int64_t dst_row_pitch);
 
+size_t flatfield_workspace_bytes(int64_t Y, int64_t X);
+int flatfield_begin(int64_t Y, int64_t X, void* ws, cudaStream_t stream);
+int flatfield_median(const void* src, int64_t Z, int64_t Y, int64_t X, void* ws, size_t ws_bytes,
+                     int64_t p0, int64_t pn, cudaStream_t stream);
+int flatfield_apply(const void* src, int64_t Z, int64_t Y, int64_t X, void* dst, int dst_dtype,
+                    void* ws, size_t ws_bytes, int64_t z0, int64_t zn, cudaStream_t stream);
+
 namespace {
 
 constexpr size_t kSlabBytes = 48u << 20;  // target output bytes per slab
@@ -161,6 +168,8 @@ struct DeviceCtx {
   size_t d_src_bytes = 0;
   void* d_dst = nullptr;
   size_t d_dst_bytes = 0;
+  void* d_ws = nullptr;  // flat-field pattern + sum
+  size_t d_ws_bytes = 0;
   void* h_in[kRing] = {nullptr, nullptr, nullptr};
   size_t h_in_bytes[kRing] = {0, 0, 0};
   void* h_out[kRing] = {nullptr, nullptr, nullptr};
@@ -478,6 +487,75 @@ int host_affine(const void* h_src, int src_dtype, int64_t sz, int64_t sy, int64_
   return run_pipeline(*c, static_cast<const char*>(h_src), reinterpret_cast<char*>(h_dst), slabs);
 }
 
+// Flat-field correction with host buffers.  Phase 1: Y-bands of the source (all Z planes of a
+// range of rows: one strided cudaMemcpy2DAsync each) are uploaded while the medians of the
+// previous band are computed.  The pattern mean needs every median, so phase 2 starts after
+// the last band: Z-slabs of the result are computed and downloaded, slab i+1 computing while slab
+// i travels.  Same three-stream pipeline as the resamplers.
+int host_flatfield(const void* h_src, int64_t Z, int64_t Y, int64_t X, void* h_dst, int dst_dtype,
+                   int device) {
+  if (!h_src || !h_dst) {
+    set_error("b2h_flatfield_u16: null pointer");
+    return B2_ERR_INVALID;
+  }
+  if (Z < 1 || Y < 1 || X < 1 || Z > 65535) {
+    set_error("b2h_flatfield_u16: invalid shape (1 <= Z <= 65535)");
+    return B2_ERR_INVALID;
+  }
+  if (dst_dtype != B2_DTYPE_F32 && dst_dtype != B2_DTYPE_F64) {
+    set_error("b2h_flatfield_u16: dst_dtype must be float32 or float64");
+    return B2_ERR_INVALID;
+  }
+  std::lock_guard<std::mutex> lock(g_mu);
+  DeviceCtx* c = nullptr;
+  int rc = get_ctx(device, &c);
+  if (rc) return rc;
+  const size_t osz = dst_dtype == B2_DTYPE_F32 ? 4 : 8;
+  const size_t plane_in = static_cast<size_t>(Y) * X * 2;
+  const size_t plane_out = static_cast<size_t>(Y) * X * osz;
+  const size_t ws_bytes = flatfield_workspace_bytes(Y, X);
+  if ((rc = grow_device(&c->d_src, &c->d_src_bytes, static_cast<size_t>(Z) * plane_in))) return rc;
+  if ((rc = grow_device(&c->d_dst, &c->d_dst_bytes, static_cast<size_t>(Z) * plane_out))) return rc;
+  if ((rc = grow_device(&c->d_ws, &c->d_ws_bytes, ws_bytes))) return rc;
+  void* d_src = c->d_src;
+  void* d_dst = c->d_dst;
+  void* d_ws = c->d_ws;
+
+  std::vector<Slab> slabs;
+  const size_t row_bytes = static_cast<size_t>(X) * 2;
+  const int64_t rows_per_band =
+      std::max<int64_t>(1, static_cast<int64_t>(kSlabBytes / (row_bytes * static_cast<size_t>(Z))));
+  for (int64_t y0 = 0; y0 < Y; y0 += rows_per_band) {
+    const int64_t cnt = std::min(rows_per_band, Y - y0);
+    Slab s;
+    Band b;
+    b.off = static_cast<size_t>(y0) * row_bytes;
+    b.pitch = plane_in;
+    b.width = static_cast<size_t>(cnt) * row_bytes;
+    b.rows = static_cast<size_t>(Z);
+    s.bands.push_back(b);
+    const bool first = y0 == 0;
+    s.launch = [=](cudaStream_t st) {
+      int r = first ? flatfield_begin(Y, X, d_ws, st) : B2_OK;
+      if (r) return r;
+      return flatfield_median(d_src, Z, Y, X, d_ws, ws_bytes, y0 * X, cnt * X, st);
+    };
+    slabs.push_back(std::move(s));
+  }
+  const int64_t per_slab = std::max<int64_t>(1, static_cast<int64_t>(kSlabBytes / plane_out));
+  for (int64_t z0 = 0; z0 < Z; z0 += per_slab) {
+    const int64_t cnt = std::min(per_slab, Z - z0);
+    Slab s;
+    s.out_off = static_cast<size_t>(z0) * plane_out;
+    s.out_bytes = static_cast<size_t>(cnt) * plane_out;
+    s.launch = [=](cudaStream_t st) {
+      return flatfield_apply(d_src, Z, Y, X, d_dst, dst_dtype, d_ws, ws_bytes, z0, cnt, st);
+    };
+    slabs.push_back(std::move(s));
+  }
+  return run_pipeline(*c, static_cast<const char*>(h_src), static_cast<char*>(h_dst), slabs);
+}
+
 int host_release() {
   std::lock_guard<std::mutex> lock(g_mu);
   for (int d = 0; d < kMaxDevices; ++d) {
@@ -489,6 +567,7 @@ int host_release() {
     c.events.clear();
     if (c.d_src) cudaFree(c.d_src);
     if (c.d_dst) cudaFree(c.d_dst);
+    if (c.d_ws) cudaFree(c.d_ws);
     for (int r = 0; r < kRing; ++r) {
       if (c.h_in[r]) cudaFreeHost(c.h_in[r]);
       if (c.h_out[r]) cudaFreeHost(c.h_out[r]);

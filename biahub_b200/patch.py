@@ -20,6 +20,9 @@ _TARGETS = {
     "biahub.register": ("biahub_b200.register", [
         "apply_affine_transform", "convert_transform_to_ants", "convert_transform_to_numpy"]),
     "biahub.stabilize": ("biahub_b200.stabilize", ["apply_stabilization_transform"]),
+    # reference biahub/flat_field.py:299-310 looks `_flat_field_czyx` up at call time
+    "biahub.flat_field": ("biahub_b200.flat_field", [
+        "flat_field_zyx", "flat_field_correction", "_flat_field_czyx"]),
     # duplicate helpers (reference biahub/registration/utils.py:774-853)
     "biahub.registration.utils": ("biahub_b200.register", ["apply_affine_transform"]),
 }

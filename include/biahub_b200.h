@@ -40,6 +40,7 @@ extern "C" {
  * biahub/register.py:266; uint16 is shipped as uint16 and converted in registers) */
 #define B2_DTYPE_U16 0
 #define B2_DTYPE_F32 1
+#define B2_DTYPE_F64 2 /* flat-field results only */
 
 /* boundary rule of the affine warp */
 #define B2_BOUNDARY_CONSTANT 0 /* scipy.ndimage mode="constant", cval=0 (biahub/register.py:272) */
@@ -134,6 +135,22 @@ B2_API int b2h_affine3d(const void* h_src, int src_dtype, int64_t sz, int64_t sy
                  float* h_dst, int64_t oz, int64_t oy, int64_t ox,
                  const double* M12, const int64_t* crop_start,
                  int order, int boundary, int scrub_nonfinite, int device);
+
+/*
+ * Flat-field correction (reference biahub/flat_field.py:105-122 `flat_field_zyx`, :152-166
+ * `_flat_field_czyx`; the pipeline stage before deskew): pattern = median over Z of every (y, x)
+ * pixel, out = (double(src) / pattern) * mean(pattern), rounded to float32 (what the czyx adapter
+ * stores) or kept as float64 (what `flat_field_zyx` returns).  uint16 sources, 1 <= z <= 65535.
+ * Bit-identical to numpy.  `workspace`: b2_flatfield_workspace(y, x) bytes of device memory,
+ * 256-byte aligned (holds the float32 pattern and the pattern sum).
+ */
+B2_API size_t b2_flatfield_workspace(int64_t y, int64_t x);
+B2_API int b2_flatfield_u16(const void* src, int64_t z, int64_t y, int64_t x, void* dst, int dst_dtype,
+                     void* workspace, size_t workspace_bytes, void* stream);
+/* host-buffer variant: Y-bands are uploaded while the medians of the previous band are computed,
+ * Z-slabs of the result are downloaded while the next slab is computed */
+B2_API int b2h_flatfield_u16(const void* h_src, int64_t z, int64_t y, int64_t x, void* h_dst,
+                      int dst_dtype, int device);
 
 /* release the per-process pinned/device staging pools of the b2h_* calls */
 B2_API int b2h_release(void);

@@ -113,3 +113,20 @@ def load_reference_settings():
         pkg.__path__ = [os.path.join(REFERENCE_ROOT, "biahub")]
         sys.modules["biahub"] = pkg
     return importlib.import_module("biahub.settings")
+
+
+def load_reference_flat_field():
+    """Return the reference's ``biahub.flat_field`` module (numpy only; same stubs as deskew).
+
+    ``flat_field_zyx`` / ``_flat_field_czyx`` (reference biahub/flat_field.py:105-122, 152-166)
+    are plain numpy and run unmodified."""
+    load_reference_deskew()  # installs the third-party stand-ins
+    saved_pkg = sys.modules.get("biahub")
+    pkg = types.ModuleType("biahub")
+    pkg.__path__ = [os.path.join(REFERENCE_ROOT, "biahub")]
+    sys.modules["biahub"] = pkg
+    try:
+        return importlib.import_module("biahub.flat_field")
+    finally:
+        if saved_pkg is not None:
+            sys.modules["biahub"] = saved_pkg
