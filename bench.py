@@ -63,6 +63,10 @@ WORKLOADS = {
     "stabilize_c4": dict(kind="stabilize", shape=(64, 2048, 2048), dtype="float32", units=16,
                          e2e_units=4, ncu_traffic=2.1177e9,
                          desc="C4 stabilize float32 (Z=64,Y=2048,X=2048) fractional XYZ translations"),
+    # the pipeline stage before deskew (not part of BASELINE's metric; here for
+    # its roofline line): median over Z + exact float64 divide, uint16 -> float32
+    "flatfield": dict(kind="flatfield", shape=(800, 300, 2048), dtype="uint16", units=8, e2e_units=2,
+                      desc="flat-field (median over Z, divide) uint16 (Z=800,Y=300,X=2048) -> float32"),
     # configs[4] (per position/timepoint unit): deskew (C2 parameters) then register the deskewed
     # float32 (100,2048,1813) volume onto the same shape, intermediate resident in HBM
     "chain_c5": dict(kind="chain", shape=(800, 300, 2048), dtype="uint16", units=8,
@@ -259,6 +263,8 @@ def run_b200(args, w, rank, world, local_rank):
                     srcs[u], mats[u], out_shape, ls_angle_deg=w["ls_angle_deg"],
                     px_to_scan_ratio=w["px_to_scan_ratio"], keep_overhang=w["keep_overhang"],
                     average_n_slices=w["average_n_slices"])
+            elif w["kind"] == "flatfield":
+                outs[u] = b2.flat_field._flatfield_tensor(srcs[u], torch.float32)
             else:
                 outs[u] = b2.affine_warp(srcs[u], mats[u], out_shape, order=1, boundary="itk")
 
@@ -295,7 +301,7 @@ def run_b200(args, w, rank, world, local_rank):
     ms_total = float(t.item())
     ms_per_step = ms_total / args.steps
     value = world * units * out_vox / (ms_per_step * 1e-3) / 1e9
-    # one kernel launch per unit (two for the chained workload: bytes and time of both)
+    # one kernel launch per unit (two for the chained and flat-field workloads: bytes and time of both)
     launch_ms = ms_total / max(args.steps * units, 1)
 
     # ---- end to end through the reference-facing call with host buffers (pinned in, pinned out)
@@ -312,7 +318,8 @@ def run_b200(args, w, rank, world, local_rank):
         h_in.append(buf)
     del srcs, outs
     torch.cuda.empty_cache()
-    h_out = [pinned_empty(out_shape, np.float32) for _ in range(e2e_units)]
+    h_out = [pinned_empty(out_shape, np.float32) for _ in range(e2e_units if w["kind"] != "flatfield" else 0)]
+    res_ff = [None]  # flat-field returns its (pooled, pinned) result instead of filling `out`
 
     def e2e_step():
         for u in range(e2e_units):
@@ -321,6 +328,9 @@ def run_b200(args, w, rank, world, local_rank):
                     h_in[u], mats[u], out_shape, ls_angle_deg=w["ls_angle_deg"],
                     px_to_scan_ratio=w["px_to_scan_ratio"], keep_overhang=w["keep_overhang"],
                     average_n_slices=w["average_n_slices"], device=local_rank, out=h_out[u])
+            elif w["kind"] == "flatfield":
+                res_ff[0] = None
+                res_ff[0] = b2._flat_field_czyx(h_in[u][None], [0], device=local_rank)
             elif w["kind"] == "deskew":
                 b2._fast_deskew_czyx(h_in[u][None], device=f"cuda:{local_rank}", out=h_out[u],
                                      ls_angle_deg=w["ls_angle_deg"],
@@ -348,8 +358,9 @@ def run_b200(args, w, rank, world, local_rank):
     e2e_s = float(te.item())
     e2e_value = world * e2e_units * e2e_steps * out_vox / e2e_s / 1e9
     esz = 2 if w["dtype"] == "uint16" else 4
-    check = (float(h_out[0].ravel()[:: max(1, h_out[0].size // 1000)].astype(np.float64).sum())
-             if e2e_units else None)
+    first_out = res_ff[0][0] if w["kind"] == "flatfield" and res_ff[0] is not None else (h_out[0] if h_out else None)
+    check = (float(first_out.ravel()[:: max(1, first_out.size // 1000)].astype(np.float64).sum())
+             if e2e_units and first_out is not None else None)
     # same call with ordinary (pageable) numpy arrays in and a fresh array out: what the
     # reference's process_single_position hands over; staged through the library's pinned rings
     pageable_value = None
@@ -399,7 +410,7 @@ def run_b200(args, w, rank, world, local_rank):
                 "h2d_bytes_per_step": int(e2e_units * Z * Y * X * esz),
                 "d2h_bytes_per_step": int(e2e_units * out_vox * 4),
                 "steps": e2e_steps, "units_per_step_per_gpu": e2e_units,
-                "api": ("biahub_b200._fast_deskew_czyx" if w["kind"] == "deskew" else "biahub_b200.affine_warp (apply_affine_transform/apply_stabilization_transform body)")
+                "api": ("biahub_b200._flat_field_czyx" if w["kind"] == "flatfield" else "biahub_b200._fast_deskew_czyx" if w["kind"] == "deskew" else "biahub_b200.affine_warp (apply_affine_transform/apply_stabilization_transform body)")
                        + " with pinned host in/out -> b2h_* C-ABI",
                 "gpu_launches": int(launches_e2e), "checksum": check, "numa_node": numa.get("numa_node"),
                 "pageable_value": None if pageable_value is None else round(pageable_value, 3)},
@@ -408,7 +419,7 @@ def run_b200(args, w, rank, world, local_rank):
                      # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the
                      # committed ncu --set full capture of this workload (profiles/r1_*.txt)
                      "traffic": w.get("ncu_traffic"),
-                     "kernel": {"deskew": "deskew_tma_kernel", "chain": "deskew_tma_kernel + affine_zsep_kernel (bytes and time of both)"}.get(w["kind"], "affine_brick_kernel" if w.get("generic") else "affine_zsep_kernel"),
+                     "kernel": {"deskew": "deskew_tma_kernel", "chain": "deskew_tma_kernel + affine_zsep_kernel (bytes and time of both)", "flatfield": "flatfield_median_kernel + flatfield_apply_kernel (time of both; algorithmic bytes = one read + one write, the 5-pass radix select re-reads the source)"}.get(w["kind"], "affine_brick_kernel" if w.get("generic") else "affine_zsep_kernel"),
                      "algorithmic_bytes_per_launch": int(bytes_unit),
                      "launch_ms": round(launch_ms, 4), "peak_source": peak_src},
     }
@@ -445,6 +456,18 @@ def cpu_sample(w):
         desc = (f"1 unit restricted to X={xs} of {X} coverslip columns (uint16 {Z}x{Y}x{xs}); CPU torch "
                 f"port of reference fast_deskew_zyx stages (biahub/deskew.py:505-536), {threads} threads")
         return fn, int(np.prod(out_shape)), threads, desc
+    if w["kind"] == "flatfield":
+        from oracle import flatfield_oracle as fo
+
+        xs = min(X, 128)
+        raw = rng.integers(90, 1200, size=(Z, Y, xs), dtype=np.uint16)
+
+        def fn():
+            return fo.flat_field_czyx_oracle(raw[None], [0])
+
+        desc = (f"1 unit restricted to X={xs} of {X} columns (uint16 {Z}x{Y}x{xs}); numpy port of "
+                f"reference _flat_field_czyx (biahub/flat_field.py:105-166), 1 thread")
+        return fn, Z * Y * xs, 1, desc
     zs = min(Z, 4)
     vol = (rng.random((zs + 2, Y, X), dtype=np.float32) * 4095).astype(np.float32)
     M = ao.register_matrix_c3((Z, Y, X)) if w["kind"] == "register" else stabilize_matrices(2)[1]
