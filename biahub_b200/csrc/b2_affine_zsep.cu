@@ -218,11 +218,13 @@ __global__ void __launch_bounds__(kZsThreads) __maxnreg__(kZsTY == 16 ? B2_ZSEP_
       p.dst + static_cast<int64_t>(zb) * plane_out + static_cast<int64_t>(y0) * p.dpitch + x0;
   const bool full_tile = (y0 + kZsTY <= p.oy) && (x0 + kZsTX <= p.ox);  // CTA-uniform
 
+  const bool lane0 = (tid & 31) == 0;
   // reduce the next plane of the producer's sequence to one value per point (p_last)
   auto fetch_plane = [&]() {
     const uint32_t stage = seq % kZsStages;
     mbar_wait_u32(full0 + stage * 8u, (seq / kZsStages) & 1u);
     const uint32_t base = stage0 + stage * g.stage_bytes;
+    const uint32_t base1 = base + pitch;
     float v[kZsPPT];
     if (ORDER == 0) {
 #pragma unroll
@@ -239,12 +241,10 @@ __global__ void __launch_bounds__(kZsThreads) __maxnreg__(kZsTY == 16 ? B2_ZSEP_
         float t00[4], t01[4], t10[4], t11[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const uint32_t a0 = base + off[i0 + j];
-          const uint32_t a1 = a0 + pitch;
-          t00[j] = lds_elem<T>(a0);
-          t01[j] = lds_elem<T>(a0 + sizeof(T));
-          t10[j] = lds_elem<T>(a1);
-          t11[j] = lds_elem<T>(a1 + sizeof(T));
+          t00[j] = lds_elem<T>(base + off[i0 + j]);
+          t01[j] = lds_elem<T>(base + off[i0 + j] + sizeof(T));
+          t10[j] = lds_elem<T>(base1 + off[i0 + j]);
+          t11[j] = lds_elem<T>(base1 + off[i0 + j] + sizeof(T));
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(kZsThreads) __maxnreg__(kZsTY == 16 ? B2_ZSEP_
       p_last[i] = v[i];
     }
     __syncwarp();
-    if ((tid & 31) == 0) mbar_arrive_u32(empty0 + stage * 8u);
+    if (lane0) mbar_arrive_u32(empty0 + stage * 8u);
     ++seq;
   };
 
