@@ -399,9 +399,10 @@ def run_b200(args, w, rank, world, local_rank):
         "higher_is_better": True,
         "scaling": "weak",
         "vs_baseline": None,
-        "dtype": "f32" if w["dtype"] == "float32" else "u16->f32",
+        # the arithmetic type of the path (sources are stored as uint16 or float32, see config)
+        "dtype": "f32" if w["kind"] != "flatfield" else "f64",
         "data": "synthetic (uniform noise, seeded, generated on device; e2e copies of the same volumes in pinned host memory)",
-        "config": {"workload": w["desc"], "units_per_step_per_gpu": units,
+        "config": {"workload": w["desc"], "source_dtype": w["dtype"], "units_per_step_per_gpu": units,
                    "out_shape": list(out_shape), "sharding": "independent (position,t,c) units per rank, no collective",
                    "l2": f"inputs+outputs resident per step = {units * bytes_unit / 1e9:.1f} GB >> 126 MB L2 (no flush needed)"},
         "clocks": clocks,

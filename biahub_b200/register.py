@@ -111,10 +111,38 @@ class ItkAffineParameters:
         return convert_transform_to_numpy(self)
 
     def apply_to_image(self, image, reference=None, interpolation="linear"):
-        image = np.asarray(image)
-        shape = image.shape if reference is None else np.shape(reference)
-        return affine_warp(image, self.as_matrix(), tuple(shape),
-                           order=_interpolation_order(interpolation), boundary="itk")
+        """``ants.ANTsTransform.apply_to_image`` for the estimation loops that warp inside their
+        optimisation (reference biahub/optimize_registration.py:111, registration/ants.py:204,
+        registration/beads.py:117,194,920,966, estimate_registration.py:192,332).  Accepts numpy
+        arrays or image objects with ``.numpy()`` (ANTs images); an image object in gives an
+        image object out, so ``t.apply_to_image(ants.from_numpy(a), reference=r).numpy()`` works
+        unchanged."""
+        wrapped = hasattr(image, "numpy") and not isinstance(image, np.ndarray)
+        arr = np.asarray(image.numpy() if wrapped else image)
+        if reference is None:
+            shape = arr.shape
+        else:
+            shape = tuple(reference.shape) if hasattr(reference, "shape") else np.shape(reference)
+        out = affine_warp(arr, self.as_matrix(), tuple(int(v) for v in shape),
+                          order=_interpolation_order(interpolation), boundary="itk")
+        return WarpedImage(out) if wrapped else out
+
+
+class WarpedImage:
+    """Minimal image object returned by ``ItkAffineParameters.apply_to_image`` when it was given
+    one: ``.numpy()``, ``.shape`` and ``np.asarray`` support, which is all the reference's call
+    sites use of the ANTs image that comes back."""
+
+    def __init__(self, array):
+        self._array = array
+        self.shape = array.shape
+        self.dimension = array.ndim
+
+    def numpy(self):
+        return self._array
+
+    def __array__(self, dtype=None, copy=None):
+        return self._array if dtype is None else self._array.astype(dtype)
 
 
 def convert_transform_to_ants(T_numpy: np.ndarray):

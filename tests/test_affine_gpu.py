@@ -298,3 +298,30 @@ def test_find_overlapping_volume():
     mask = ao.affine_oracle_numpy(np.ones(shape, np.float32), M2, shape, 1, "itk") > 0
     assert mask[z, y, x].all()                  # the crop lies inside the warped support
     assert (z.stop - z.start) * (y.stop - y.start) * (x.stop - x.start) > 0.5 * mask.sum()
+
+
+def test_ants_transform_shim_apply_to_image():
+    """The estimation loops call ``convert_transform_to_ants(M).apply_to_image(ants_img,
+    reference=ants_img).numpy()`` (reference biahub/optimize_registration.py:111): the shim takes
+    image objects or arrays and resamples with the ITK boundary rule on the GPU."""
+    import biahub_b200 as b2
+
+    class FakeAntsImage:  # what ants.from_numpy returns, as far as the call sites use it
+        def __init__(self, a):
+            self._a, self.shape = a, a.shape
+
+        def numpy(self):
+            return self._a
+
+    rng = np.random.default_rng(11)
+    mov = (rng.random((10, 40, 48), dtype=np.float32) * 100).astype(np.float32)
+    ref = np.zeros((12, 36, 52), np.float32)
+    M = np.eye(4)
+    M[:3, 3] = (0.5, -1.25, 2.0)
+    M[1, 1] = 1.05
+    t = b2.convert_transform_to_ants(M)
+    want = b2.affine_warp(mov, M, ref.shape, order=1, boundary="itk")
+    got = t.apply_to_image(FakeAntsImage(mov), reference=FakeAntsImage(ref))
+    assert np.array_equal(got.numpy(), want) and got.shape == ref.shape
+    assert np.array_equal(t.apply_to_image(mov, reference=ref), want)
+    assert np.array_equal(np.asarray(got), want)
