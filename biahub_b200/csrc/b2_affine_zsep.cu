@@ -33,6 +33,7 @@ struct ZsepGeom {
   int BY, BX;       // brick extent per plane (elements)
   int stage_bytes;  // BY*BX*sizeof(T) rounded up to 128
   int zchunk;       // output planes per CTA (<= kZsMaxChunk)
+  int unit_z;       // m00 == 1 exactly: source planes advance one per output plane
 };
 
 template <typename T>
@@ -219,13 +220,12 @@ __global__ void __launch_bounds__(kZsThreads) __maxnreg__(kZsTY == 16 ? B2_ZSEP_
   const bool full_tile = (y0 + kZsTY <= p.oy) && (x0 + kZsTX <= p.ox);  // CTA-uniform
 
   const bool lane0 = (tid & 31) == 0;
-  // reduce the next plane of the producer's sequence to one value per point (p_last)
-  auto fetch_plane = [&]() {
+  // reduce the next plane of the producer's sequence to one in-plane-interpolated value per point
+  auto load_plane = [&](float (&v)[kZsPPT]) {
     const uint32_t stage = seq % kZsStages;
     mbar_wait_u32(full0 + stage * 8u, (seq / kZsStages) & 1u);
     const uint32_t base = stage0 + stage * g.stage_bytes;
     const uint32_t base1 = base + pitch;
-    float v[kZsPPT];
     if (ORDER == 0) {
 #pragma unroll
       for (int i = 0; i < kZsPPT; ++i) {
@@ -273,19 +273,71 @@ __global__ void __launch_bounds__(kZsThreads) __maxnreg__(kZsTY == 16 ? B2_ZSEP_
         }
       }
     }
+    __syncwarp();
+    if (lane0) mbar_arrive_u32(empty0 + stage * 8u);
+    ++seq;
+  };
+  auto fetch_plane = [&]() {  // general path: keep the last two planes
+    float v[kZsPPT];
+    load_plane(v);
 #pragma unroll
     for (int i = 0; i < kZsPPT; ++i) {
       p_prev[i] = p_last[i];
       p_last[i] = v[i];
     }
-    __syncwarp();
-    if (lane0) mbar_arrive_u32(empty0 + stage * 8u);
-    ++seq;
+  };
+  auto store_plane = [&](const float (&o)[kZsPPT]) {
+    if (full_tile) {
+#pragma unroll
+      for (int i = 0; i < kZsPPT; ++i) st_global_cs(out_tile + ooff[i], o[i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < kZsPPT; ++i)
+        if (ooff[i] >= 0) st_global_cs(out_tile + ooff[i], o[i]);
+    }
   };
 
   for (int zl = 0; zl < nz; ++zl, out_tile += plane_out) {
     const int4 e = ztab[zl];
     float o[kZsPPT];
+    if (ORDER == 1 && g.unit_z && e.x == s_last && e.y == e.x + 1) {
+      // ---- regular run (m00 == 1: every output plane takes the NEXT source plane as its upper
+      // tap and hands it on as the lower tap of the following one).  Per arriving plane and
+      // point: 4 LDS + 4 FMA in-plane, o = fma(w1, v, pend), pend' = w0' * v — the same
+      // operations in the same order as the general path, without its two-plane register
+      // rotation, tap-table branches and per-plane bookkeeping.
+      float pend[kZsPPT];
+      {
+        const float wz0 = __int_as_float(e.z);
+#pragma unroll
+        for (int i = 0; i < kZsPPT; ++i) pend[i] = __fmul_rn(wz0, p_last[i]);
+      }
+      float wz1 = __int_as_float(e.w);
+      int s = s_last;
+      for (;;) {
+        float v[kZsPPT];
+        load_plane(v);
+        ++s;
+        const bool more = zl + 1 < nz;
+        const int4 en = ztab[more ? zl + 1 : zl];
+#pragma unroll
+        for (int i = 0; i < kZsPPT; ++i) o[i] = __fmaf_rn(wz1, v[i], pend[i]);
+        store_plane(o);
+        if (!(more && en.x == s && en.y == s + 1)) {  // CTA-uniform
+#pragma unroll
+          for (int i = 0; i < kZsPPT; ++i) p_prev[i] = p_last[i] = v[i];
+          break;
+        }
+        const float wn0 = __int_as_float(en.z);
+#pragma unroll
+        for (int i = 0; i < kZsPPT; ++i) pend[i] = __fmul_rn(wn0, v[i]);
+        wz1 = __int_as_float(en.w);
+        ++zl;
+        out_tile += plane_out;
+      }
+      s_last = s;
+      continue;
+    }
     if (e.x < 0) {  // this output plane maps outside the source: zeros
 #pragma unroll
       for (int i = 0; i < kZsPPT; ++i) o[i] = 0.0f;
@@ -308,14 +360,7 @@ __global__ void __launch_bounds__(kZsThreads) __maxnreg__(kZsTY == 16 ? B2_ZSEP_
           o[i] = __fmaf_rn(wz1, p_last[i], __fmul_rn(wz0, p_prev[i]));
       }
     }
-    if (full_tile) {
-#pragma unroll
-      for (int i = 0; i < kZsPPT; ++i) st_global_cs(out_tile + ooff[i], o[i]);
-    } else {
-#pragma unroll
-      for (int i = 0; i < kZsPPT; ++i)
-        if (ooff[i] >= 0) st_global_cs(out_tile + ooff[i], o[i]);
-    }
+    store_plane(o);
   }
 }
 
@@ -347,6 +392,7 @@ static bool zsep_geometry(const AffineParams& p, int kZsTY, ZsepGeom* g, size_t*
   g->BY = BY;
   g->BX = BX;
   g->stage_bytes = stage;
+  g->unit_z = (m[0] == 1.0) ? 1 : 0;
   *smem_bytes = static_cast<size_t>(stage) * kZsStages + 256;  // + barriers + alignment
   return true;
 }
