@@ -78,17 +78,25 @@ __global__ void __launch_bounds__(kZsThreads) __maxnreg__(kZsTY == 16 ? B2_ZSEP_
                        const __grid_constant__ AffineParams p, const ZsepGeom g) {
   constexpr int kZsPPT = (kZsTY * kZsTX) / kZsConsumers;  // output points per consumer thread
   extern __shared__ uint8_t smem_raw[];
-  // per output plane of this CTA: {i0 (or -1 when outside), i1, bits(w0), bits(w1)}
-  __shared__ int4 ztab[kZsMaxChunk];
 
   constexpr int kVec = 16 / static_cast<int>(sizeof(T));
-  // dynamic shared memory: [full barriers | empty barriers | pad to 128 B] [stage ring]; all
+  // dynamic shared memory: [full barriers | empty barriers | pad to 128 B] [z tap table]
+  // [stage ring]; the z tap table holds per output plane of this CTA
+  // {i0 (or -1 when outside), i1, bits(w0), bits(w1)}; all
   // addresses derive from ONE register (a static __shared__ barrier array makes the compiler
   // re-derive the shared-window address with S2R/LEA inside the plane loop)
   const uint32_t bars = (smem_u32(smem_raw) + 127u) & ~127u;
   const uint32_t full0 = bars;
   const uint32_t empty0 = bars + 8u * kZsStages;
-  const uint32_t stage0 = bars + 128u;
+  const uint32_t ztab0 = bars + 128u;
+  const uint32_t stage0 = ztab0 + 16u * kZsMaxChunk;
+  auto ztab_at = [&](int zl) {
+    int4 e;
+    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(e.x), "=r"(e.y), "=r"(e.z), "=r"(e.w)
+                 : "r"(ztab0 + 16u * static_cast<uint32_t>(zl)));
+    return e;
+  };
   const int tid = threadIdx.x;
   const int y0 = blockIdx.y * kZsTY;
   const int x0 = blockIdx.x * kZsTX;
@@ -143,7 +151,9 @@ __global__ void __launch_bounds__(kZsThreads) __maxnreg__(kZsTY == 16 ? B2_ZSEP_
     e.y = tz.i1;
     e.z = __float_as_int(__fsub_rn(1.0f, tz.w));
     e.w = __float_as_int(tz.w);
-    ztab[tid] = e;
+    asm volatile("st.shared.v4.s32 [%0], {%1, %2, %3, %4};" ::"r"(ztab0 + 16u * static_cast<uint32_t>(tid)),
+                 "r"(e.x), "r"(e.y), "r"(e.z), "r"(e.w)
+                 : "memory");
   }
   __syncthreads();
 
@@ -153,7 +163,7 @@ __global__ void __launch_bounds__(kZsThreads) __maxnreg__(kZsTY == 16 ? B2_ZSEP_
     int s_last = INT_MIN;
     uint32_t seq = 0;
     for (int zl = 0; zl < nz; ++zl) {
-      const int4 e = ztab[zl];
+      const int4 e = ztab_at(zl);
       if (e.x < 0) continue;
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -226,16 +236,20 @@ __global__ void __launch_bounds__(kZsThreads) __maxnreg__(kZsTY == 16 ? B2_ZSEP_
     mbar_wait_u32(full0 + stage * 8u, (seq / kZsStages) & 1u);
     const uint32_t base = stage0 + stage * g.stage_bytes;
     const uint32_t base1 = base + pitch;
+    // every lane's taps have been consumed when the warp-wide vote below completes: it doubles
+    // as the convergence point before lane 0 releases the stage (a __syncwarp() here makes ptxas
+    // treat the loop as divergent and re-materialise its uniform registers per plane)
+    bool bad = false;
     if (ORDER == 0) {
 #pragma unroll
       for (int i = 0; i < kZsPPT; ++i) {
         float t = lds_elem<T>(base + off[i]);
         if (SCRUB && sizeof(T) == 4) t = scrub_value(t);
         v[i] = ((inmask >> i) & 1u) ? t : 0.0f;
+        bad |= (__float_as_uint(v[i]) == 0xffffffffu);  // never true: ties the vote to the loads
       }
     } else {
       // groups of 4 points: 16 taps in flight, then 4 x (FMUL + 3 FFMA)
-      bool bad = false;
 #pragma unroll
       for (int i0 = 0; i0 < kZsPPT; i0 += 4) {
         float t00[4], t01[4], t10[4], t11[4];
@@ -254,26 +268,27 @@ __global__ void __launch_bounds__(kZsThreads) __maxnreg__(kZsTY == 16 ? B2_ZSEP_
           bad |= !(fabsf(v[i]) <= FLT_MAX);
         }
       }
-      if (sizeof(T) == 4 && bad) {
-        // a NaN/inf tap was involved (possibly with zero weight): redo with the scrub
-        // (np.nan_to_num semantics), re-reading the taps; without SCRUB only the dummy taps of
-        // outside points are fixed
+    }
+    const bool any_bad = __any_sync(0xffffffffu, bad);
+    if (ORDER == 1 && sizeof(T) == 4 && any_bad) {
+      // a NaN/inf tap was involved (possibly with zero weight): redo with the scrub
+      // (np.nan_to_num semantics), re-reading the taps; without SCRUB only the dummy taps of
+      // outside points are fixed.  Warp-uniform branch; the stage is released after it.
 #pragma unroll
-        for (int i = 0; i < kZsPPT; ++i) {
-          if (SCRUB) {
-            const uint32_t a0 = base + off[i];
-            const uint32_t a1 = a0 + pitch;
-            v[i] = __fmaf_rn(w11[i], scrub_value(lds_elem<T>(a1 + sizeof(T))),
-                             __fmaf_rn(w10[i], scrub_value(lds_elem<T>(a1)),
-                                       __fmaf_rn(w01[i], scrub_value(lds_elem<T>(a0 + sizeof(T))),
-                                                 __fmul_rn(w00[i], scrub_value(lds_elem<T>(a0))))));
-          } else if (!((inmask >> i) & 1u)) {
-            v[i] = 0.0f;
-          }
+      for (int i = 0; i < kZsPPT; ++i) {
+        if (SCRUB) {
+          const uint32_t a0 = base + off[i];
+          const uint32_t a1 = a0 + pitch;
+          v[i] = __fmaf_rn(w11[i], scrub_value(lds_elem<T>(a1 + sizeof(T))),
+                           __fmaf_rn(w10[i], scrub_value(lds_elem<T>(a1)),
+                                     __fmaf_rn(w01[i], scrub_value(lds_elem<T>(a0 + sizeof(T))),
+                                               __fmul_rn(w00[i], scrub_value(lds_elem<T>(a0))))));
+        } else if (!((inmask >> i) & 1u)) {
+          v[i] = 0.0f;
         }
       }
+      __syncwarp();
     }
-    __syncwarp();
     if (lane0) mbar_arrive_u32(empty0 + stage * 8u);
     ++seq;
   };
@@ -298,7 +313,7 @@ __global__ void __launch_bounds__(kZsThreads) __maxnreg__(kZsTY == 16 ? B2_ZSEP_
   };
 
   for (int zl = 0; zl < nz; ++zl, out_tile += plane_out) {
-    const int4 e = ztab[zl];
+    const int4 e = ztab_at(zl);
     float o[kZsPPT];
     if (ORDER == 1 && g.unit_z && e.x == s_last && e.y == e.x + 1) {
       // ---- regular run (m00 == 1: every output plane takes the NEXT source plane as its upper
@@ -319,7 +334,7 @@ __global__ void __launch_bounds__(kZsThreads) __maxnreg__(kZsTY == 16 ? B2_ZSEP_
         load_plane(v);
         ++s;
         const bool more = zl + 1 < nz;
-        const int4 en = ztab[more ? zl + 1 : zl];
+        const int4 en = ztab_at(more ? zl + 1 : zl);
 #pragma unroll
         for (int i = 0; i < kZsPPT; ++i) o[i] = __fmaf_rn(wz1, v[i], pend[i]);
         store_plane(o);
@@ -393,7 +408,7 @@ static bool zsep_geometry(const AffineParams& p, int kZsTY, ZsepGeom* g, size_t*
   g->BX = BX;
   g->stage_bytes = stage;
   g->unit_z = (m[0] == 1.0) ? 1 : 0;
-  *smem_bytes = static_cast<size_t>(stage) * kZsStages + 256;  // + barriers + alignment
+  *smem_bytes = static_cast<size_t>(stage) * kZsStages + 256 + 16 * kZsMaxChunk;  // + barriers, z table, alignment
   return true;
 }
 
