@@ -25,7 +25,7 @@ namespace b2 {
 constexpr int kZsTX = 64;
 constexpr int kZsConsumers = 256;
 constexpr int kZsThreads = kZsConsumers + 32;  // + one producer warp
-constexpr int kZsStages = 4;
+constexpr int kZsMaxStages = 8;  // ring depth is chosen per launch (ZsepGeom::stages, 3..8)
 constexpr int kZsRowsPerPass = kZsConsumers / kZsTX;
 constexpr int kZsMaxChunk = 128;  // output planes per CTA (size of the z tap table)
 
@@ -34,6 +34,7 @@ struct ZsepGeom {
   int stage_bytes;  // BY*BX*sizeof(T) rounded up to 128
   int zchunk;       // output planes per CTA (<= kZsMaxChunk)
   int unit_z;       // m00 == 1 exactly: source planes advance one per output plane
+  int stages;       // depth of the plane ring (3..kZsMaxStages)
 };
 
 template <typename T>
@@ -87,7 +88,7 @@ __global__ void __launch_bounds__(kZsThreads) __maxnreg__(kZsTY == 16 ? B2_ZSEP_
   // re-derive the shared-window address with S2R/LEA inside the plane loop)
   const uint32_t bars = (smem_u32(smem_raw) + 127u) & ~127u;
   const uint32_t full0 = bars;
-  const uint32_t empty0 = bars + 8u * kZsStages;
+  const uint32_t empty0 = bars + 8u * kZsMaxStages;
   const uint32_t ztab0 = bars + 128u;
   const uint32_t stage0 = ztab0 + 16u * kZsMaxChunk;
   auto ztab_at = [&](int zl) {
@@ -137,7 +138,7 @@ __global__ void __launch_bounds__(kZsThreads) __maxnreg__(kZsTY == 16 ? B2_ZSEP_
 
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < kZsStages; ++s) {
+    for (int s = 0; s < g.stages; ++s) {
       mbar_init_u32(full0 + 8u * s, 1);
       mbar_init_u32(empty0 + 8u * s, kZsConsumers / 32);
     }
@@ -161,7 +162,8 @@ __global__ void __launch_bounds__(kZsThreads) __maxnreg__(kZsTY == 16 ? B2_ZSEP_
     // ============ producer warp: walks the plane sequence, lane 0 issues the TMA loads ============
     const bool issuer = (tid == kZsConsumers);
     int s_last = INT_MIN;
-    uint32_t seq = 0;
+    uint32_t stage = 0, phase = 0;  // ring position of the next plane, parity of its round
+    bool first_round = true;
     for (int zl = 0; zl < nz; ++zl) {
       const int4 e = ztab_at(zl);
       if (e.x < 0) continue;
@@ -169,15 +171,18 @@ __global__ void __launch_bounds__(kZsThreads) __maxnreg__(kZsTY == 16 ? B2_ZSEP_
       for (int h = 0; h < 2; ++h) {
         const int s = h ? e.y : e.x;
         if (s > s_last) {
-          const uint32_t stage = seq % kZsStages;
-          if (seq >= kZsStages) mbar_wait_u32(empty0 + 8u * stage, ((seq / kZsStages) - 1) & 1);
+          if (!first_round) mbar_wait_u32(empty0 + 8u * stage, phase ^ 1u);
           if (issuer) {
             mbar_expect_tx_u32(full0 + 8u * stage, static_cast<uint32_t>(g.BY) * g.BX * sizeof(T));
             tma_load_3d_u32(stage0 + stage * g.stage_bytes, &src_map, full0 + 8u * stage, bx0, by0, s);
           }
           __syncwarp();
           s_last = s;
-          ++seq;
+          if (++stage == static_cast<uint32_t>(g.stages)) {
+            stage = 0;
+            phase ^= 1u;
+            first_round = false;
+          }
         }
       }
     }
@@ -223,7 +228,7 @@ __global__ void __launch_bounds__(kZsThreads) __maxnreg__(kZsTY == 16 ? B2_ZSEP_
 #pragma unroll
   for (int i = 0; i < kZsPPT; ++i) p_prev[i] = p_last[i] = 0.0f;
   int s_last = INT_MIN;
-  uint32_t seq = 0;
+  uint32_t stage = 0, phase = 0;  // ring position of the next plane to consume, parity of its round
   const int64_t plane_out = static_cast<int64_t>(p.oy) * p.dpitch;
   float* __restrict__ out_tile =
       p.dst + static_cast<int64_t>(zb) * plane_out + static_cast<int64_t>(y0) * p.dpitch + x0;
@@ -232,8 +237,7 @@ __global__ void __launch_bounds__(kZsThreads) __maxnreg__(kZsTY == 16 ? B2_ZSEP_
   const bool lane0 = (tid & 31) == 0;
   // reduce the next plane of the producer's sequence to one in-plane-interpolated value per point
   auto load_plane = [&](float (&v)[kZsPPT]) {
-    const uint32_t stage = seq % kZsStages;
-    mbar_wait_u32(full0 + stage * 8u, (seq / kZsStages) & 1u);
+    mbar_wait_u32(full0 + stage * 8u, phase);
     const uint32_t base = stage0 + stage * g.stage_bytes;
     const uint32_t base1 = base + pitch;
     // every lane's taps have been consumed when the warp-wide vote below completes: it doubles
@@ -290,7 +294,10 @@ __global__ void __launch_bounds__(kZsThreads) __maxnreg__(kZsTY == 16 ? B2_ZSEP_
       __syncwarp();
     }
     if (lane0) mbar_arrive_u32(empty0 + stage * 8u);
-    ++seq;
+    if (++stage == static_cast<uint32_t>(g.stages)) {
+      stage = 0;
+      phase ^= 1u;
+    }
   };
   auto fetch_plane = [&]() {  // general path: keep the last two planes
     float v[kZsPPT];
@@ -402,13 +409,19 @@ static bool zsep_geometry(const AffineParams& p, int kZsTY, ZsepGeom* g, size_t*
   auto stage_of = [&](int bx) { return (BY * bx * static_cast<int>(sizeof(T)) + 127) / 128 * 128; };
   if (BY > 256 || BX > 256) return false;
   const int stage = stage_of(BX);
-  if (stage * kZsStages > 96 * 1024) return false;
+  // ring depth: as deep as 70 KB per CTA allow (3 CTAs per SM), 8 at most; the consumers run at
+  // ~0.7 us per plane and a TMA round trip is ~1.5 us, 4 stages left them waiting (ncu: long
+  // scoreboard 3.7 per issue)
+  int stages = (70 * 1024) / stage;
+  if (stages > kZsMaxStages) stages = kZsMaxStages;
+  if (stages < 3) return false;
+  g->stages = stages;
   if (static_cast<int64_t>(kZsTY) * p.dpitch >= (1LL << 31)) return false;
   g->BY = BY;
   g->BX = BX;
   g->stage_bytes = stage;
   g->unit_z = (m[0] == 1.0) ? 1 : 0;
-  *smem_bytes = static_cast<size_t>(stage) * kZsStages + 256 + 16 * kZsMaxChunk;  // + barriers, z table, alignment
+  *smem_bytes = static_cast<size_t>(stage) * stages + 256 + 16 * kZsMaxChunk;  // + barriers, z table, alignment
   return true;
 }
 
