@@ -414,6 +414,15 @@ static bool zsep_geometry(const AffineParams& p, int kZsTY, ZsepGeom* g, size_t*
   // scoreboard 3.7 per issue)
   int stages = (70 * 1024) / stage;
   if (stages > kZsMaxStages) stages = kZsMaxStages;
+  // large bricks (rotation / scale halos): a deeper ring lets neighbouring CTAs drift apart in z
+  // and their shared halo rows fall out of L2 (C3: DRAM reads 2.24 -> 2.61 GB at 8 stages);
+  // measured best: 6 for C3's 8.8 KB planes, 8 for C4's 4.9 KB planes
+  if (stage > 6 * 1024 && stages > 6) stages = 6;
+  {
+    const char* e = getenv("B2_ZSEP_STAGES");  // sweep override
+    const int v = e ? atoi(e) : 0;
+    if (v >= 3 && v < stages) stages = v;
+  }
   if (stages < 3) return false;
   g->stages = stages;
   if (static_cast<int64_t>(kZsTY) * p.dpitch >= (1LL << 31)) return false;
