@@ -37,7 +37,7 @@ from .register import (  # noqa: F401
     rescale_voxel_size,
 )
 from .flat_field import _flat_field_czyx, flat_field_correction, flat_field_zyx  # noqa: F401
-from .pipeline import deskew_then_register  # noqa: F401
+from .pipeline import deskew_then_register, flatfield_then_deskew  # noqa: F401
 from .stabilize import apply_stabilization_transform  # noqa: F401
 
 __version__ = "0.1.0"

@@ -108,3 +108,16 @@ def test_mantis_sized_properties():
     want = (cols.astype(np.float64) / pat_cols[None, :] * mean).astype(np.float32)
     got = out[:, ys, xs].cpu().numpy()
     assert np.array_equal(got, want)
+
+
+def test_flatfield_then_deskew_equals_the_two_steps():
+    """Chained unit (flat-field output stays in HBM) == _fast_deskew_czyx(_flat_field_czyx(raw))."""
+    rng = np.random.default_rng(21)
+    raw = (100 + rng.poisson(40, size=(96, 30, 128))).astype(np.uint16)
+    kw = dict(ls_angle_deg=30.0, px_to_scan_ratio=0.386, keep_overhang=False, average_n_slices=3)
+    flat = b2._flat_field_czyx(raw[None], [0])
+    want = b2._fast_deskew_czyx(flat, **kw)[0]
+    got = b2.flatfield_then_deskew(raw, **kw)
+    assert got.dtype == np.float32 and np.array_equal(got, want)
+    dev = b2.flatfield_then_deskew(_cuda_u16(raw), **kw)
+    assert dev.is_cuda and np.array_equal(dev.cpu().numpy(), want)
