@@ -121,3 +121,23 @@ def test_flatfield_then_deskew_equals_the_two_steps():
     assert got.dtype == np.float32 and np.array_equal(got, want)
     dev = b2.flatfield_then_deskew(_cuda_u16(raw), **kw)
     assert dev.is_cuda and np.array_equal(dev.cpu().numpy(), want)
+
+
+def test_host_pipeline_many_bands_and_slabs():
+    """b2h_flatfield_u16 with a volume that spans several upload bands and download slabs
+    (48 MB each): pageable and pinned inputs, float32 and float64 results == the device API."""
+    from biahub_b200._device import pinned_empty
+
+    Z, Y, X = 96, 700, 1024   # 138 MB uint16 -> 3 bands; 275 MB float32 -> 6 slabs
+    g = torch.Generator(device="cuda").manual_seed(12)
+    t = torch.randint(80, 3000, (Z, Y, X), generator=g, device="cuda", dtype=torch.int32).to(torch.uint16)
+    want32 = b2.flat_field._flatfield_tensor(t, torch.float32).cpu().numpy()
+    host = t.view(torch.int16).cpu().numpy().view(np.uint16)
+    got = b2._flat_field_czyx(host[None], [0])
+    assert np.array_equal(got[0], want32)
+    pinned = pinned_empty(host.shape, np.uint16)
+    pinned[...] = host
+    assert np.array_equal(b2._flat_field_czyx(pinned[None], [0])[0], want32)
+    del got
+    want64 = b2.flat_field._flatfield_tensor(t[:40], torch.float64).cpu().numpy()
+    assert np.array_equal(b2.flat_field_zyx(host[:40]), want64)
