@@ -18,15 +18,22 @@
 
 namespace b2 {
 
-// tile height kZsTY is a template parameter (16 or 32 rows -> 4 or 8 output points per thread)
 #ifndef B2_ZSEP_MAXREG
 #define B2_ZSEP_MAXREG 72  // 3 CTAs (27 warps) per SM
 #endif
-constexpr int kZsTX = 64;
+// Output tile: 16 x 64 points (y x x), lanes along x.  LY variant (matrices that map output y
+// onto source x, e.g. the 90-degree rotations of the manual registration): 64 x 16, lanes along
+// y, so that a warp's taps run along a brick ROW (conflict-free shared-memory reads; with lanes
+// along x they walk a brick COLUMN: 8-way bank conflicts, 0.33 of the roofline); the output
+// plane is transposed through shared memory to keep the global stores coalesced.
+constexpr int kZsTileLanes = 64;  // tile extent along the lane axis
+constexpr int kZsTileOther = 16;  // tile extent along the other in-plane axis
+constexpr int kZsPPT = (kZsTileLanes * kZsTileOther) / 256;  // output points per consumer thread
+constexpr int kZsOutPitch = kZsTileOther + 1;  // LY: padded pitch of the transposed output tile
 constexpr int kZsConsumers = 256;
 constexpr int kZsThreads = kZsConsumers + 32;  // + one producer warp
 constexpr int kZsMaxStages = 8;  // ring depth is chosen per launch (ZsepGeom::stages, 3..8)
-constexpr int kZsRowsPerPass = kZsConsumers / kZsTX;
+constexpr int kZsRowsPerPass = kZsConsumers / kZsTileLanes;
 constexpr int kZsMaxChunk = 128;  // output planes per CTA (size of the z tap table)
 
 struct ZsepGeom {
@@ -59,9 +66,10 @@ __device__ __forceinline__ double coord_yx(double yf, double xf, const double* m
 
 // Rare path: the host-side bound on the brick size was too tight for this tile (never expected):
 // every thread of the CTA resamples the tile straight from global memory.
-template <typename T, int ORDER, int BOUNDARY, bool SCRUB, int kZsTY>
+template <typename T, int ORDER, int BOUNDARY, bool SCRUB, bool LY>
 __device__ __noinline__ void zsep_tile_from_global(const AffineParams& p, int y0, int x0, int zb,
                                                    int ze) {
+  constexpr int kZsTY = LY ? kZsTileLanes : kZsTileOther, kZsTX = LY ? kZsTileOther : kZsTileLanes;
   const int n = (ze - zb) * kZsTY * kZsTX;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const int x = x0 + i % kZsTX;
@@ -73,11 +81,11 @@ __device__ __noinline__ void zsep_tile_from_global(const AffineParams& p, int y0
   }
 }
 
-template <typename T, int ORDER, int BOUNDARY, bool SCRUB, int kZsTY>
-__global__ void __launch_bounds__(kZsThreads) __maxnreg__(kZsTY == 16 ? B2_ZSEP_MAXREG : 112)
+template <typename T, int ORDER, int BOUNDARY, bool SCRUB, bool LY>
+__global__ void __launch_bounds__(kZsThreads, 3)
     affine_zsep_kernel(const __grid_constant__ CUtensorMap src_map,
                        const __grid_constant__ AffineParams p, const ZsepGeom g) {
-  constexpr int kZsPPT = (kZsTY * kZsTX) / kZsConsumers;  // output points per consumer thread
+  constexpr int kZsTY = LY ? kZsTileLanes : kZsTileOther, kZsTX = LY ? kZsTileOther : kZsTileLanes;
   extern __shared__ uint8_t smem_raw[];
 
   constexpr int kVec = 16 / static_cast<int>(sizeof(T));
@@ -90,7 +98,10 @@ __global__ void __launch_bounds__(kZsThreads) __maxnreg__(kZsTY == 16 ? B2_ZSEP_
   const uint32_t full0 = bars;
   const uint32_t empty0 = bars + 8u * kZsMaxStages;
   const uint32_t ztab0 = bars + 128u;
-  const uint32_t stage0 = ztab0 + 16u * kZsMaxChunk;
+  // LY: two transposed output tiles (double-buffered: one consumer barrier per plane)
+  constexpr uint32_t kOutTileBytes = LY ? kZsTileLanes * kZsOutPitch * 4u : 0u;
+  const uint32_t otile0 = ztab0 + 16u * kZsMaxChunk;
+  const uint32_t stage0 = (otile0 + 2u * kOutTileBytes + 127u) & ~127u;
   auto ztab_at = [&](int zl) {
     int4 e;
     asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];"
@@ -132,7 +143,7 @@ __global__ void __launch_bounds__(kZsThreads) __maxnreg__(kZsTY == 16 ? B2_ZSEP_
   const int bx_hi = __double2int_rd(fmax(-big, fmin(big, cx_max))) + 2;
   const bool brick_ok = (by_hi - by0) < g.BY && (bx_hi - bx0) < g.BX;  // CTA-uniform
   if (!brick_ok) {
-    zsep_tile_from_global<T, ORDER, BOUNDARY, SCRUB, kZsTY>(p, y0, x0, zb, ze);
+    zsep_tile_from_global<T, ORDER, BOUNDARY, SCRUB, LY>(p, y0, x0, zb, ze);
     return;
   }
 
@@ -190,9 +201,8 @@ __global__ void __launch_bounds__(kZsThreads) __maxnreg__(kZsTY == 16 ? B2_ZSEP_
   }
 
   // ================================= consumer threads =================================
-  const int lx = tid % kZsTX;
-  const int ly = tid / kZsTX;
-  const int x = x0 + lx;
+  const int ll = tid % kZsTileLanes;  // position along the lane axis (x, or y when LY)
+  const int lo = tid / kZsTileLanes;  // first position along the other axis
   const uint32_t pitch = static_cast<uint32_t>(g.BX) * sizeof(T);
 
   uint32_t off[kZsPPT];  // byte offset of tap (i0y, i0x) inside a stage
@@ -201,15 +211,18 @@ __global__ void __launch_bounds__(kZsThreads) __maxnreg__(kZsTY == 16 ? B2_ZSEP_
   uint32_t inmask = 0;  // bit i: point i samples inside the source
 #pragma unroll
   for (int i = 0; i < kZsPPT; ++i) {
-    const int yy = ly + kZsRowsPerPass * i;
-    const int y = y0 + yy;
+    const int oo = lo + kZsRowsPerPass * i;
+    const int yy = LY ? ll : oo, xx = LY ? oo : ll;
+    const int y = y0 + yy, x = x0 + xx;
     const bool live = (y < p.oy) && (x < p.ox);
     const double yf = static_cast<double>(y + p.cy);
     const double xf = static_cast<double>(x + p.cx);
     const AxisTap ty = resolve_axis<ORDER, BOUNDARY>(coord_yx(yf, xf, p.m + 4), p.sy);
     const AxisTap tx = resolve_axis<ORDER, BOUNDARY>(coord_yx(yf, xf, p.m + 8), p.sx);
     const bool in = live && ty.inside && tx.inside;
-    ooff[i] = live ? yy * p.dpitch + lx : -1;
+    // !LY: global offset of the point relative to the tile origin (-1 = no voxel);
+    //  LY: byte offset of the point in the transposed output tile in shared memory
+    ooff[i] = LY ? (yy * kZsOutPitch + xx) * 4 : (live ? yy * p.dpitch + xx : -1);
     inmask |= in ? (1u << i) : 0u;
     off[i] = in ? static_cast<uint32_t>(ty.i0 - by0) * pitch +
                       static_cast<uint32_t>(tx.i0 - bx0) * static_cast<uint32_t>(sizeof(T))
@@ -308,7 +321,30 @@ __global__ void __launch_bounds__(kZsThreads) __maxnreg__(kZsTY == 16 ? B2_ZSEP_
       p_last[i] = v[i];
     }
   };
+  // LY store phase: thread t writes column t % 16 of the rows t / 16 + 16 j (64-byte row segments)
+  uint32_t oparity = 0;
+  const int sc = tid % kZsTileOther, sr = tid / kZsTileOther;
+  const bool sc_ok = x0 + sc < p.ox;
   auto store_plane = [&](const float (&o)[kZsPPT]) {
+    if (LY) {
+      // transpose through shared memory: lanes run along y here, the global rows run along x
+      const uint32_t buf = otile0 + oparity * kOutTileBytes;
+      oparity ^= 1u;
+#pragma unroll
+      for (int i = 0; i < kZsPPT; ++i)
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(buf + static_cast<uint32_t>(ooff[i])), "f"(o[i]));
+      asm volatile("bar.sync 1, %0;" ::"n"(kZsConsumers) : "memory");  // consumers only
+#pragma unroll
+      for (int j = 0; j < kZsTileLanes / (kZsConsumers / kZsTileOther); ++j) {
+        const int r = sr + j * (kZsConsumers / kZsTileOther);
+        float v;
+        asm volatile("ld.shared.f32 %0, [%1];"
+                     : "=f"(v)
+                     : "r"(buf + static_cast<uint32_t>((r * kZsOutPitch + sc) * 4)));
+        if (sc_ok && y0 + r < p.oy) st_global_cs(out_tile + static_cast<int64_t>(r) * p.dpitch + sc, v);
+      }
+      return;
+    }
     if (full_tile) {
 #pragma unroll
       for (int i = 0; i < kZsPPT; ++i) st_global_cs(out_tile + ooff[i], o[i]);
@@ -390,7 +426,8 @@ __global__ void __launch_bounds__(kZsThreads) __maxnreg__(kZsTY == 16 ? B2_ZSEP_
 // host side
 // ---------------------------------------------------------------------------------------------
 template <typename T>
-static bool zsep_geometry(const AffineParams& p, int kZsTY, ZsepGeom* g, size_t* smem_bytes) {
+static bool zsep_geometry(const AffineParams& p, bool ly, ZsepGeom* g, size_t* smem_bytes) {
+  const int kZsTY = ly ? kZsTileLanes : kZsTileOther, kZsTX = ly ? kZsTileOther : kZsTileLanes;
   const double* m = p.m;
   if (m[1] != 0.0 || m[2] != 0.0 || m[4] != 0.0 || m[8] != 0.0) return false;
   if (!(m[0] > 0.0)) return false;
@@ -430,11 +467,12 @@ static bool zsep_geometry(const AffineParams& p, int kZsTY, ZsepGeom* g, size_t*
   g->BX = BX;
   g->stage_bytes = stage;
   g->unit_z = (m[0] == 1.0) ? 1 : 0;
-  *smem_bytes = static_cast<size_t>(stage) * stages + 256 + 16 * kZsMaxChunk;  // + barriers, z table, alignment
+  *smem_bytes = static_cast<size_t>(stage) * stages + 384 + 16 * kZsMaxChunk +
+                (ly ? 2 * kZsTileLanes * kZsOutPitch * 4 : 0);  // + barriers, z table, alignment
   return true;
 }
 
-template <typename T, int ORDER, int BOUNDARY, bool SCRUB, int kZsTY>
+template <typename T, int ORDER, int BOUNDARY, bool SCRUB, bool LY>
 static int launch_zsep(const AffineParams& p, ZsepGeom g, size_t smem_bytes, cudaStream_t stream) {
   EncodeTiledFn encode = get_encode_tiled();
   if (!encode) {
@@ -460,6 +498,7 @@ static int launch_zsep(const AffineParams& p, ZsepGeom g, size_t smem_bytes, cud
   }
   int sms = 148;
   sm_count(&sms);
+  constexpr int kZsTY = LY ? kZsTileLanes : kZsTileOther, kZsTX = LY ? kZsTileOther : kZsTileLanes;
   const int tiles_x = (p.ox + kZsTX - 1) / kZsTX;
   const int tiles_y = (p.oy + kZsTY - 1) / kZsTY;
   const int64_t tiles = static_cast<int64_t>(tiles_x) * tiles_y;
@@ -475,7 +514,7 @@ static int launch_zsep(const AffineParams& p, ZsepGeom g, size_t smem_bytes, cud
   if (tiles_y > 65535 || grid_z > 65535)
     return affine_gather_launch(p, sizeof(T) == 2 ? B2_DTYPE_U16 : B2_DTYPE_F32, stream);
 
-  auto kern = affine_zsep_kernel<T, ORDER, BOUNDARY, SCRUB, kZsTY>;
+  auto kern = affine_zsep_kernel<T, ORDER, BOUNDARY, SCRUB, LY>;
   B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                static_cast<int>(smem_bytes)));
   const dim3 grid(tiles_x, tiles_y, grid_z);
@@ -499,28 +538,17 @@ static bool is_integer_translation(const AffineParams& p) {
   return true;
 }
 
-// Tile height: 32 rows (8 points per thread) amortise the per-plane barrier / bookkeeping
-// instructions over twice the points and shrink the in-plane halo; 16 rows keep 3 CTAs per SM.
-static int zsep_tile_rows() {
-  static const int ty = [] {
-    const char* e = getenv("B2_ZSEP_TY");
-    const int v = e ? atoi(e) : 0;
-    return (v == 16 || v == 32) ? v : 16;
-  }();
-  return ty;
-}
-
-template <typename T, int TY>
-static int zsep_typed_ty(const AffineParams& p, cudaStream_t stream, bool* eligible) {
+template <typename T, bool LY>
+static int zsep_typed_ly(const AffineParams& p, cudaStream_t stream, bool* eligible) {
   ZsepGeom g{};
   size_t smem = 0;
-  *eligible = zsep_geometry<T>(p, TY, &g, &smem);
+  *eligible = zsep_geometry<T>(p, LY, &g, &smem);
   if (!*eligible) return B2_ERR_UNSUPPORTED;
   const bool scrub = p.scrub && sizeof(T) == 4;
   const int order = (p.order == 1 && is_integer_translation(p)) ? 0 : p.order;
 #define B2_ZS(ORD, BND)                                           \
-  (scrub ? launch_zsep<T, ORD, BND, true, TY>(p, g, smem, stream) \
-         : launch_zsep<T, ORD, BND, false, TY>(p, g, smem, stream))
+  (scrub ? launch_zsep<T, ORD, BND, true, LY>(p, g, smem, stream) \
+         : launch_zsep<T, ORD, BND, false, LY>(p, g, smem, stream))
   if (order == 0)
     return p.boundary == B2_BOUNDARY_CONSTANT ? B2_ZS(0, B2_BOUNDARY_CONSTANT)
                                               : B2_ZS(0, B2_BOUNDARY_ITK);
@@ -531,11 +559,18 @@ static int zsep_typed_ty(const AffineParams& p, cudaStream_t stream, bool* eligi
 
 template <typename T>
 static int zsep_typed(const AffineParams& p, cudaStream_t stream, bool* eligible) {
-  if (zsep_tile_rows() == 32) {
-    const int rc = zsep_typed_ty<T, 32>(p, stream, eligible);
+  // lanes follow the output axis along which the SOURCE x coordinate moves fastest
+  // (m[9] = d src_x / d out_y, m[10] = d src_x / d out_x)
+  static const int force = [] {
+    const char* e = getenv("B2_ZSEP_LANES_Y");  // A/B switch: 0 / 1, unset = automatic
+    return e ? atoi(e) : -1;
+  }();
+  const bool ly = force >= 0 ? force != 0 : fabs(p.m[9]) > fabs(p.m[10]);
+  if (ly) {
+    const int rc = zsep_typed_ly<T, true>(p, stream, eligible);
     if (*eligible) return rc;
   }
-  return zsep_typed_ty<T, 16>(p, stream, eligible);
+  return zsep_typed_ly<T, false>(p, stream, eligible);
 }
 
 int affine_zsep_launch(const AffineParams& p, int src_dtype, cudaStream_t stream, bool* eligible) {

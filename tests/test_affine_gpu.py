@@ -325,3 +325,41 @@ def test_ants_transform_shim_apply_to_image():
     assert np.array_equal(got.numpy(), want) and got.shape == ref.shape
     assert np.array_equal(t.apply_to_image(mov, reference=ref), want)
     assert np.array_equal(np.asarray(got), want)
+
+
+@pytest.mark.parametrize("mname", ["rot90", "rot90_scale_fliplr", "rot270_shift", "rot60"])
+def test_lanes_along_y_variant(mname):
+    """Matrices that map output y onto source x (the manual-registration family: scaling @ rotate90
+    @ fliplr, reference biahub/estimate_registration.py:174-189) take the zsep kernel with lanes
+    along y and a shared-memory transposed store: must match the oracle and the gather kernel,
+    including ragged tiles (shape not a multiple of 64 x 16) and a cropped output."""
+    import torch
+
+    import biahub_b200 as b2
+    from biahub_b200 import _cabi, affine_warp
+
+    shape = (20, 150, 204)   # source rows 16-byte aligned (TMA-eligible); output ragged on purpose
+    out_shape = (18, 210, 141)
+    vol = _vol(shape, seed=31)
+    mats = {
+        "rot90": b2.get_3D_rotation_matrix(shape, 90),
+        "rot90_scale_fliplr": (b2.get_3D_rescaling_matrix(shape, (1.0, 1.07, 1.07))
+                               @ b2.get_3D_rotation_matrix(shape, 90) @ b2.get_3D_fliplr_matrix(shape)),
+        "rot270_shift": ao.translation_matrix_zyx((0.4, 3.25, -11.5)) @ b2.get_3D_rotation_matrix(shape, 270),
+        "rot60": b2.get_3D_rotation_matrix(shape, 60),
+    }
+    M = mats[mname]
+    assert abs(M[2, 1]) > abs(M[2, 2])  # d src_x / d out_y dominates: the LY variant is selected
+    t = _to_cuda(vol)
+    for order in (0, 1):
+        for boundary in ("constant", "itk"):
+            want = ao.affine_oracle_numpy(vol, M, out_shape, order, boundary)
+            a = affine_warp(t, M, out_shape, order=order, boundary=boundary, _path=_cabi.PATH_TMA)
+            b = affine_warp(t, M, out_shape, order=order, boundary=boundary, _path=_cabi.PATH_GATHER)
+            _compare(a.cpu().numpy(), want, order, name=f"{mname}/o{order}/{boundary}")
+            if order == 0:
+                assert torch.equal(a, b)
+    crop = (slice(2, 15), slice(7, 190), slice(5, 133))
+    want = ao.affine_oracle_numpy(vol, M, out_shape, 1, "itk")[crop]
+    got = affine_warp(vol, M, out_shape, order=1, boundary="itk", crop_output_slicing=crop)
+    _compare(got, want, 1, name=f"{mname}/crop")
