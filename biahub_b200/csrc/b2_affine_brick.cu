@@ -17,11 +17,17 @@
 namespace b2 {
 
 constexpr int kBrTZ = 8;
-constexpr int kBrTY = 16;
-constexpr int kBrTX = 32;
+// In-plane tile: 16 (y) x 32 (x) with lanes along x; LY variant 32 (y) x 16 (x) with lanes along y
+// for matrices that map output y onto source x (90-degree in-plane rotations: with lanes along x
+// a warp's taps walk a brick column, 8-way bank conflicts) — its output goes through a padded
+// shared-memory tile so that the global stores stay row-contiguous.
+constexpr int kBrLanes = 32;  // tile extent along the lane axis
+constexpr int kBrOther = 16;  // tile extent along the other in-plane axis
 constexpr int kBrThreads = 256;
-constexpr int kBrCols = (kBrTY * kBrTX) / kBrThreads;  // (y, x) columns per thread
-constexpr int kBrRowStep = kBrThreads / kBrTX;          // y distance between a thread's columns
+constexpr int kBrCols = (kBrLanes * kBrOther) / kBrThreads;  // (y, x) columns per thread
+constexpr int kBrRowStep = kBrThreads / kBrLanes;            // distance between a thread's columns
+constexpr int kBrOutPitch = kBrOther + 1;                    // LY: padded row pitch of the staged output
+constexpr int kBrStageBytes = kBrTZ * kBrLanes * kBrOutPitch * 4;
 constexpr float kEdge = 2.0e-3f;
 constexpr float kMagic = 12582912.0f;  // 1.5 * 2^23: (v + kMagic) - kMagic rounds v to nearest
 
@@ -121,6 +127,17 @@ __device__ __noinline__ float brick_sample_exact(const AffineParams& p, uint32_t
   return lerp_w(p0, p1, tz.w);
 }
 
+// one output voxel: straight to global memory (streaming), or — LY — into the staged output tile
+// in shared memory (generic store)
+template <bool LY>
+__device__ __forceinline__ void brick_put(float* o, float v) {
+  if (LY) {
+    *o = v;
+  } else {
+    st_global_cs(o, v);
+  }
+}
+
 struct BrickCol {
   uint32_t brick, plane_b, row_b;
   int64_t out_plane;
@@ -134,7 +151,7 @@ struct BrickCol {
 // written (not strictly interior, or a non-finite tap turned up): the caller finishes those on the
 // exact path.  CHECK = false: the whole tile is known to be strictly interior (decided once per
 // CTA from the brick hull) and the per-voxel test is compiled out.  ~40 instructions per voxel.
-template <typename T, bool SCRUB, bool CHECK>
+template <typename T, bool SCRUB, bool CHECK, bool LY>
 __device__ __forceinline__ uint32_t brick_column_linear(const BrickCol& c, const float (&mid)[3],
                                                         const float (&half)[3],
                                                         float* __restrict__ out) {
@@ -199,12 +216,12 @@ __device__ __forceinline__ uint32_t brick_column_linear(const BrickCol& c, const
       v = lerp_w(lerp_w(lerp_w(v000, v001, wx), lerp_w(v010, v011, wx), wy),
                  lerp_w(lerp_w(r0, r1, wx), lerp_w(r2, r3, wx), wy), wz);
     }
-    st_global_cs(o, v);
+    brick_put<LY>(o, v);
   }
   return rest;
 }
 
-template <typename T, int ORDER, int BOUNDARY, bool SCRUB>
+template <typename T, int ORDER, int BOUNDARY, bool SCRUB, bool LY>
 __global__ void __launch_bounds__(kBrThreads, 4)
     affine_brick_kernel(const __grid_constant__ CUtensorMap src_map,
                         const __grid_constant__ AffineParams p,
@@ -212,7 +229,11 @@ __global__ void __launch_bounds__(kBrThreads, 4)
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t bar;
   constexpr int kVec = 16 / static_cast<int>(sizeof(T));
-  const uint32_t brick = (smem_u32(smem_raw) + 127u) & ~127u;
+  constexpr int kBrTY = LY ? kBrLanes : kBrOther, kBrTX = LY ? kBrOther : kBrLanes;
+  uint8_t* smem_al = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
+  const uint32_t brick = smem_u32(smem_al);
+  // LY: staged output tile [kBrTZ][kBrTY][kBrOutPitch] behind the brick
+  float* stage_out = reinterpret_cast<float*>(smem_al + ((g.bytes + 127) / 128) * 128);
 
   // z-fastest rasterisation: consecutive CTAs share z-halo planes
   const int tz_i = blockIdx.x % tiles_z;
@@ -268,26 +289,21 @@ __global__ void __launch_bounds__(kBrThreads, 4)
   const bool brick_ok = (s_geo[6] & 1) != 0;
   const bool tile_in = (s_geo[6] & 2) != 0;
   if (s_geo[6] & 4) {  // the whole tile maps outside the source: zeros, nothing to load
-    const int lx_ = threadIdx.x % kBrTX, ly_ = threadIdx.x / kBrTX;
-    if (x0 + lx_ < p.ox) {
-#pragma unroll
-      for (int c = 0; c < kBrCols; ++c) {
-        const int y = y0 + ly_ + c * kBrRowStep;
-        if (y >= p.oy) continue;
-        float* o = p.dst + (static_cast<int64_t>(z0) * p.oy + y) * p.dpitch + (x0 + lx_);
-        for (int k = 0; k < nz; ++k, o += static_cast<int64_t>(p.oy) * p.dpitch) st_global_cs(o, 0.0f);
-      }
+    for (int i = threadIdx.x; i < nz * kBrTY * kBrTX; i += kBrThreads) {
+      const int xx = i % kBrTX, yy = (i / kBrTX) % kBrTY, k = i / (kBrTX * kBrTY);
+      if (x0 + xx < p.ox && y0 + yy < p.oy)
+        st_global_cs(p.dst + (static_cast<int64_t>(z0 + k) * p.oy + y0 + yy) * p.dpitch + x0 + xx, 0.0f);
     }
     return;
   }
 
-  const int lx = threadIdx.x % kBrTX, ly = threadIdx.x / kBrTX;
-  const int x = x0 + lx;
+  const int lane = threadIdx.x % kBrLanes, oth = threadIdx.x / kBrLanes;
 
   if (!brick_ok) {  // host bound too tight for this tile (never expected): straight from global
 #pragma unroll
     for (int c = 0; c < kBrCols; ++c) {
-      const int y = y0 + ly + c * kBrRowStep;
+      const int o2 = oth + c * kBrRowStep;
+      const int y = y0 + (LY ? lane : o2), x = x0 + (LY ? o2 : lane);
       if (x < p.ox && y < p.oy)
         for (int k = 0; k < nz; ++k)
           p.dst[(static_cast<int64_t>(z0 + k) * p.oy + y) * p.dpitch + x] =
@@ -313,22 +329,27 @@ __global__ void __launch_bounds__(kBrThreads, 4)
   const uint32_t es = static_cast<uint32_t>(sizeof(T));
   const uint32_t row_b = static_cast<uint32_t>(g.BX) * es;
   const uint32_t plane_b = static_cast<uint32_t>(g.BY) * row_b;
-  const int64_t out_plane = static_cast<int64_t>(p.oy) * p.dpitch;
-
   mbar_wait(&bar, 0);
 
+  // output voxel (k, yy, xx) of the tile goes to out + k * out_plane: global memory, or the
+  // staged tile in shared memory (LY)
+  const int64_t out_plane = LY ? static_cast<int64_t>(kBrTY * kBrOutPitch)
+                               : static_cast<int64_t>(p.oy) * p.dpitch;
 #pragma unroll
   for (int c = 0; c < kBrCols; ++c) {
-    const int yy = ly + c * kBrRowStep;
-    const int y = y0 + yy;
+    const int o2 = oth + c * kBrRowStep;
+    const int yy = LY ? lane : o2, xx = LY ? o2 : lane;
+    const int y = y0 + yy, x = x0 + xx;
     if (x >= p.ox || y >= p.oy) continue;
-    // column start (fp32, brick-local): tile origin + yy*col1 + lx*col2
+    // column start (fp32, brick-local): tile origin + yy*col1 + xx*col2
     float u0[3];
 #pragma unroll
     for (int d = 0; d < 3; ++d)
-      u0[d] = __fmaf_rn(static_cast<float>(lx), mcol[d][2],
+      u0[d] = __fmaf_rn(static_cast<float>(xx), mcol[d][2],
                         __fmaf_rn(static_cast<float>(yy), mcol[d][1], c0l[d]));
-    float* __restrict__ out = p.dst + (static_cast<int64_t>(z0) * p.oy + y) * p.dpitch + x;
+    float* __restrict__ out =
+        LY ? stage_out + yy * kBrOutPitch + xx
+           : p.dst + (static_cast<int64_t>(z0) * p.oy + y) * p.dpitch + x;
     uint32_t todo = 0;  // bit k: voxel k is not strictly interior -> handled after the hot loop
     float* __restrict__ o = out;
 
@@ -338,9 +359,9 @@ __global__ void __launch_bounds__(kBrThreads, 4)
                         mcol[2][0]};
       uint32_t rest;
       if (tile_in) {
-        rest = brick_column_linear<T, SCRUB, false>(cc, mid, half, out);
+        rest = brick_column_linear<T, SCRUB, false, LY>(cc, mid, half, out);
       } else {
-        rest = brick_column_linear<T, SCRUB, true>(cc, mid, half, out);
+        rest = brick_column_linear<T, SCRUB, true, LY>(cc, mid, half, out);
       }
       // voxels near a decision edge, outside the source, or with non-finite taps: exact path
       while (rest) {
@@ -355,7 +376,7 @@ __global__ void __launch_bounds__(kBrThreads, 4)
         const float v = outside ? 0.0f
                                 : brick_sample_exact<T, ORDER, BOUNDARY, SCRUB>(
                                       p, brick, b0[0], b0[1], b0[2], g.BY, g.BX, z0 + k, y, x);
-        st_global_cs(out + k * out_plane, v);
+        brick_put<LY>(out + k * out_plane, v);
       }
       continue;
     }
@@ -412,7 +433,7 @@ __global__ void __launch_bounds__(kBrThreads, 4)
           continue;
         }
       }
-      st_global_cs(o, v);
+      brick_put<LY>(o, v);
     }
     // ---- voxels near a decision edge / outside the source: exact float64 path
     while (todo) {
@@ -427,7 +448,17 @@ __global__ void __launch_bounds__(kBrThreads, 4)
       const float v = outside ? 0.0f
                               : brick_sample_exact<T, ORDER, BOUNDARY, SCRUB>(
                                     p, brick, b0[0], b0[1], b0[2], g.BY, g.BX, z0 + k, y, x);
-      st_global_cs(out + k * out_plane, v);
+      brick_put<LY>(out + k * out_plane, v);
+    }
+  }
+  if (LY) {
+    // staged tile -> global memory: lanes along x again (16 columns = 64-byte row segments)
+    __syncthreads();
+    for (int i = threadIdx.x; i < nz * kBrTY * kBrTX; i += kBrThreads) {
+      const int xx = i % kBrTX, yy = (i / kBrTX) % kBrTY, k = i / (kBrTX * kBrTY);
+      if (x0 + xx < p.ox && y0 + yy < p.oy)
+        st_global_cs(p.dst + (static_cast<int64_t>(z0 + k) * p.oy + y0 + yy) * p.dpitch + x0 + xx,
+                     stage_out[(k * kBrTY + yy) * kBrOutPitch + xx]);
     }
   }
 }
@@ -436,7 +467,8 @@ __global__ void __launch_bounds__(kBrThreads, 4)
 // host side
 // ---------------------------------------------------------------------------------------------
 template <typename T>
-static bool brick_geometry(const AffineParams& p, BrickGeom* g, size_t* smem_bytes) {
+static bool brick_geometry(const AffineParams& p, bool ly, BrickGeom* g, size_t* smem_bytes) {
+  const int kBrTY = ly ? kBrLanes : kBrOther, kBrTX = ly ? kBrOther : kBrLanes;
   if (reinterpret_cast<uintptr_t>(p.src) % 16 != 0) return false;
   if ((static_cast<int64_t>(p.spitch) * sizeof(T)) % 16 != 0) return false;
   const int vec = 16 / sizeof(T);
@@ -471,11 +503,11 @@ static bool brick_geometry(const AffineParams& p, BrickGeom* g, size_t* smem_byt
   g->BY = ext[1];
   g->BX = BX;
   g->bytes = static_cast<int>(bytes);
-  *smem_bytes = static_cast<size_t>(bytes) + 128;
+  *smem_bytes = static_cast<size_t>(bytes) + 256 + (ly ? kBrStageBytes : 0);
   return true;
 }
 
-template <typename T, int ORDER, int BOUNDARY, bool SCRUB>
+template <typename T, int ORDER, int BOUNDARY, bool SCRUB, bool LY>
 static int launch_brick(const AffineParams& p, const BrickGeom& g, size_t smem_bytes,
                         cudaStream_t stream) {
   EncodeTiledFn encode = get_encode_tiled();
@@ -501,12 +533,13 @@ static int launch_brick(const AffineParams& p, const BrickGeom& g, size_t smem_b
               p.sz, p.sy, p.sx);
     return B2_ERR_UNSUPPORTED;
   }
+  constexpr int kBrTY = LY ? kBrLanes : kBrOther, kBrTX = LY ? kBrOther : kBrLanes;
   const int tiles_z = (p.oz + kBrTZ - 1) / kBrTZ;
   const int tiles_y = (p.oy + kBrTY - 1) / kBrTY;
   const int tiles_x = (p.ox + kBrTX - 1) / kBrTX;
   const int64_t tiles = static_cast<int64_t>(tiles_z) * tiles_y * tiles_x;
   if (tiles > 2147483647LL) return affine_gather_launch(p, sizeof(T) == 2 ? B2_DTYPE_U16 : B2_DTYPE_F32, stream);
-  auto kern = affine_brick_kernel<T, ORDER, BOUNDARY, SCRUB>;
+  auto kern = affine_brick_kernel<T, ORDER, BOUNDARY, SCRUB, LY>;
   B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                static_cast<int>(smem_bytes)));
   B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
@@ -517,22 +550,32 @@ static int launch_brick(const AffineParams& p, const BrickGeom& g, size_t smem_b
   return B2_OK;
 }
 
-template <typename T>
-static int brick_typed(const AffineParams& p, cudaStream_t stream, bool* eligible) {
+template <typename T, bool LY>
+static int brick_typed_ly(const AffineParams& p, cudaStream_t stream, bool* eligible) {
   BrickGeom g{};
   size_t smem = 0;
-  *eligible = brick_geometry<T>(p, &g, &smem);
+  *eligible = brick_geometry<T>(p, LY, &g, &smem);
   if (!*eligible) return B2_ERR_UNSUPPORTED;
   const bool scrub = p.scrub && sizeof(T) == 4;
-#define B2_BR(ORD, BND)                                        \
-  (scrub ? launch_brick<T, ORD, BND, true>(p, g, smem, stream) \
-         : launch_brick<T, ORD, BND, false>(p, g, smem, stream))
+#define B2_BR(ORD, BND)                                            \
+  (scrub ? launch_brick<T, ORD, BND, true, LY>(p, g, smem, stream) \
+         : launch_brick<T, ORD, BND, false, LY>(p, g, smem, stream))
   if (p.order == 0)
     return p.boundary == B2_BOUNDARY_CONSTANT ? B2_BR(0, B2_BOUNDARY_CONSTANT)
                                               : B2_BR(0, B2_BOUNDARY_ITK);
   return p.boundary == B2_BOUNDARY_CONSTANT ? B2_BR(1, B2_BOUNDARY_CONSTANT)
                                             : B2_BR(1, B2_BOUNDARY_ITK);
 #undef B2_BR
+}
+
+template <typename T>
+static int brick_typed(const AffineParams& p, cudaStream_t stream, bool* eligible) {
+  // lanes follow the output axis along which the SOURCE x coordinate moves fastest
+  if (fabs(p.m[9]) > fabs(p.m[10])) {
+    const int rc = brick_typed_ly<T, true>(p, stream, eligible);
+    if (*eligible) return rc;
+  }
+  return brick_typed_ly<T, false>(p, stream, eligible);
 }
 
 int affine_brick_launch(const AffineParams& p, int src_dtype, cudaStream_t stream, bool* eligible) {

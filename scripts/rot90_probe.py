@@ -26,3 +26,15 @@ run("scale 1.07 @ rot 90 @ fliplr", b2.get_3D_rescaling_matrix(shape, (1, 1.07, 
 run("rot 45", b2.get_3D_rotation_matrix(shape, 45))
 run("rot 180", b2.get_3D_rotation_matrix(shape, 180))
 run("identity + frac shift", T)
+# generic (non z-separable) matrices: brick kernel
+def oop(shape, a_deg, b_deg):
+    c = (np.array(shape) - 1) / 2.0
+    a, b = np.radians(a_deg), np.radians(b_deg)
+    Ry = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]])
+    Rx = np.array([[np.cos(b), -np.sin(b), 0], [np.sin(b), np.cos(b), 0], [0, 0, 1]])
+    R = Ry @ Rx; M = np.eye(4); M[:3, :3] = R; M[:3, 3] = c - R @ c
+    return M
+C3 = T @ b2.get_3D_rotation_matrix(shape, 7.3) @ b2.get_3D_rescaling_matrix(shape, (1, 1.07, 1.07))
+R90 = b2.get_3D_rescaling_matrix(shape, (1, 1.07, 1.07)) @ b2.get_3D_rotation_matrix(shape, 90) @ b2.get_3D_fliplr_matrix(shape)
+run("generic: C3 @ tilt(0.5,0.3)", C3 @ oop(shape, 0.5, 0.3))
+run("generic: rot90 family @ tilt", R90 @ oop(shape, 0.5, 0.3))

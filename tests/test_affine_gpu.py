@@ -363,3 +363,35 @@ def test_lanes_along_y_variant(mname):
     want = ao.affine_oracle_numpy(vol, M, out_shape, 1, "itk")[crop]
     got = affine_warp(vol, M, out_shape, order=1, boundary="itk", crop_output_slicing=crop)
     _compare(got, want, 1, name=f"{mname}/crop")
+
+
+@pytest.mark.parametrize("order", [0, 1])
+def test_generic_lanes_along_y_variant(order):
+    """Non z-separable matrix with a 90-degree in-plane part (an ESTIMATED registration on top of
+    the manual rotate90 approximation): brick kernel with lanes along y and staged stores."""
+    import torch
+
+    import biahub_b200 as b2
+    from biahub_b200 import _cabi, affine_warp
+
+    shape = (20, 150, 204)
+    out_shape = (21, 210, 141)   # partial last z tile, ragged y / x tiles
+    vol = _vol(shape, seed=33)
+    c = (np.array(shape) - 1) / 2.0
+    a, b = np.radians(1.5), np.radians(-0.8)
+    Ry = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]])
+    Rx = np.array([[np.cos(b), -np.sin(b), 0], [np.sin(b), np.cos(b), 0], [0, 0, 1]])
+    tilt = np.eye(4)
+    tilt[:3, :3] = Ry @ Rx
+    tilt[:3, 3] = c - (Ry @ Rx) @ c
+    M = (b2.get_3D_rescaling_matrix(shape, (1.0, 1.05, 1.05)) @ b2.get_3D_rotation_matrix(shape, 90)
+         @ b2.get_3D_fliplr_matrix(shape) @ tilt)
+    assert abs(M[2, 1]) > abs(M[2, 2]) and abs(M[0, 1]) + abs(M[0, 2]) > 0
+    t = _to_cuda(vol)
+    for boundary in ("constant", "itk"):
+        want = ao.affine_oracle_numpy(vol, M, out_shape, order, boundary)
+        got = affine_warp(t, M, out_shape, order=order, boundary=boundary, _path=_cabi.PATH_TMA)
+        _compare(got.cpu().numpy(), want, order, name=f"generic-ly/o{order}/{boundary}")
+        if order == 0:
+            assert torch.equal(got, affine_warp(t, M, out_shape, order=0, boundary=boundary,
+                                                _path=_cabi.PATH_GATHER))
