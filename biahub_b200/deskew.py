@@ -193,9 +193,7 @@ def _deskew_host(zyx, device, ls_angle_deg, px_to_scan_ratio, keep_overhang, ave
             t = torch.from_numpy(src).to(f"cuda:{dev}")
         res = fast_deskew_zyx(t, ls_angle_deg, px_to_scan_ratio, keep_overhang, average_n_slices,
                               overhang_fill)
-        if out is None:
-            return res.cpu().numpy()
-        out = check_out(out, tuple(res.shape))
+        out = check_out(out, tuple(res.shape))  # pooled pinned array when the caller gave none
         torch.from_numpy(out).copy_(res)
         return out
     src, code = host_source(zyx)
