@@ -411,7 +411,7 @@ def run_b200(args, w, rank, world, local_rank):
                 "h2d_bytes_per_step": int(e2e_units * Z * Y * X * esz),
                 "d2h_bytes_per_step": int(e2e_units * out_vox * 4),
                 "steps": e2e_steps, "units_per_step_per_gpu": e2e_units,
-                "api": ("biahub_b200._flat_field_czyx" if w["kind"] == "flatfield" else "biahub_b200._fast_deskew_czyx" if w["kind"] == "deskew" else "biahub_b200.affine_warp (apply_affine_transform/apply_stabilization_transform body)")
+                "api": ("biahub_b200._flat_field_czyx" if w["kind"] == "flatfield" else "biahub_b200._fast_deskew_czyx" if w["kind"] == "deskew" else "biahub_b200.deskew_then_register (b2h_deskew_affine3d)" if w["kind"] == "chain" else "biahub_b200.affine_warp (apply_affine_transform/apply_stabilization_transform body)")
                        + " with pinned host in/out -> b2h_* C-ABI",
                 "gpu_launches": int(launches_e2e), "checksum": check, "numa_node": numa.get("numa_node"),
                 "pageable_value": None if pageable_value is None else round(pageable_value, 3)},

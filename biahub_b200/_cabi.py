@@ -34,7 +34,7 @@ EXPORTS = (
     "b2_abi_version", "b2_last_error", "b2_device_count", "b2_check_device", "b2_deskew",
     "b2_affine3d", "b2_deskew_pitched", "b2_affine3d_pitched", "b2_overhang_fill_workspace", "b2_overhang_fill", "b2h_deskew",
     "b2h_affine3d", "b2h_release", "b2_launch_count",
-    "b2_flatfield_workspace", "b2_flatfield_u16", "b2h_flatfield_u16",
+    "b2_flatfield_workspace", "b2_flatfield_u16", "b2h_flatfield_u16", "b2h_deskew_affine3d",
 )
 
 
@@ -96,6 +96,10 @@ def lib() -> ctypes.CDLL:
         handle.b2_flatfield_workspace.restype = ctypes.c_size_t
         handle.b2_flatfield_u16.argtypes = [_vp, _i64, _i64, _i64, _vp, _int, _vp, ctypes.c_size_t, _vp]
         handle.b2h_flatfield_u16.argtypes = [_vp, _i64, _i64, _i64, _vp, _int, _int]
+        handle.b2h_deskew_affine3d.argtypes = [_vp, _int, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _int,
+                                               _f32, _f32, _f32, _vp, _i64, _i64, _i64,
+                                               ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_i64),
+                                               _int, _int, _int, _int]
         handle.b2h_release.restype = _int
         handle.b2_launch_count.restype = ctypes.c_uint64
         if handle.b2_abi_version() != ABI_VERSION:

@@ -77,6 +77,11 @@ int flatfield_median(const void* src, int64_t Z, int64_t Y, int64_t X, void* ws,
                      int64_t p0, int64_t pn, cudaStream_t stream);
 int flatfield_apply(const void* src, int64_t Z, int64_t Y, int64_t X, void* dst, int dst_dtype,
                     void* ws, size_t ws_bytes, int64_t z0, int64_t zn, cudaStream_t stream);
+int host_deskew_affine(const void* h_src, int src_dtype, int64_t Zi, int64_t Yi, int64_t Xi,
+                       int64_t Zavg, int64_t Yo, int64_t Xo, int64_t Zo_full, int N, float px32,
+                       float pxct32, float off32, float* h_dst, int64_t oz, int64_t oy, int64_t ox,
+                       const double* M12, const int64_t* crop_start, int order, int boundary,
+                       int scrub, int device);
 int host_flatfield(const void* h_src, int64_t Z, int64_t Y, int64_t X, void* h_dst, int dst_dtype,
                    int device);
 
@@ -214,6 +219,18 @@ int b2h_flatfield_u16(const void* h_src, int64_t z, int64_t y, int64_t x, void* 
   int rc = b2::require_device();
   if (rc) return rc;
   return b2::host_flatfield(h_src, z, y, x, h_dst, dst_dtype, device);
+}
+
+int b2h_deskew_affine3d(const void* h_src, int src_dtype, int64_t Zi, int64_t Yi, int64_t Xi,
+                        int64_t Zavg, int64_t Yo, int64_t Xo, int64_t Zo_full, int average_n_slices,
+                        float px32, float pxct32, float off32, float* h_dst, int64_t oz, int64_t oy,
+                        int64_t ox, const double* M12, const int64_t* crop_start, int order,
+                        int boundary, int scrub_nonfinite, int device) {
+  int rc = b2::require_device();
+  if (rc) return rc;
+  return b2::host_deskew_affine(h_src, src_dtype, Zi, Yi, Xi, Zavg, Yo, Xo, Zo_full,
+                                average_n_slices, px32, pxct32, off32, h_dst, oz, oy, ox, M12,
+                                crop_start, order, boundary, scrub_nonfinite, device);
 }
 
 int b2h_release(void) { return b2::host_release(); }

@@ -170,6 +170,8 @@ struct DeviceCtx {
   size_t d_dst_bytes = 0;
   void* d_ws = nullptr;  // flat-field pattern + sum
   size_t d_ws_bytes = 0;
+  void* d_mid = nullptr;  // deskewed volume of the chained deskew -> register unit
+  size_t d_mid_bytes = 0;
   void* h_in[kRing] = {nullptr, nullptr, nullptr};
   size_t h_in_bytes[kRing] = {0, 0, 0};
   void* h_out[kRing] = {nullptr, nullptr, nullptr};
@@ -487,6 +489,103 @@ int host_affine(const void* h_src, int src_dtype, int64_t sz, int64_t sy, int64_
   return run_pipeline(*c, static_cast<const char*>(h_src), reinterpret_cast<char*>(h_dst), slabs);
 }
 
+// Chained deskew -> register with host buffers (BASELINE.json configs[4]):
+// the deskewed float32 volume lives only on the device (16-byte aligned row pitch, TMA-eligible
+// source of the warp).  One pipeline: the tilt-row band of deskew slab i is uploaded while slab
+// i-1 is deskewed; as soon as the deskewed planes an output plane range needs exist, that range
+// is warped and its download starts — upload, both kernels and download overlap.
+int host_deskew_affine(const void* h_src, int src_dtype, int64_t Zi, int64_t Yi, int64_t Xi,
+                       int64_t Zavg, int64_t Yo, int64_t Xo, int64_t Zo_full, int N, float px32,
+                       float pxct32, float off32, float* h_dst, int64_t oz, int64_t oy, int64_t ox,
+                       const double* M12, const int64_t* crop_start, int order, int boundary,
+                       int scrub, int device) {
+  if (!h_src || !h_dst || !M12) {
+    set_error("b2h_deskew_affine3d: null pointer");
+    return B2_ERR_INVALID;
+  }
+  if (src_dtype != B2_DTYPE_U16 && src_dtype != B2_DTYPE_F32) {
+    set_error("b2h_deskew_affine3d: unknown src_dtype %d", src_dtype);
+    return B2_ERR_INVALID;
+  }
+  if (Zi < 2 || Yi < 1 || Xi < 1 || Zavg < 1 || Yo < 1 || Xo < 1 || N < 1 || Zo_full != Yi ||
+      Zavg != (Zo_full + N - 1) / N || oz < 0 || oy < 0 || ox < 0) {
+    set_error("b2h_deskew_affine3d: invalid shape");
+    return B2_ERR_INVALID;
+  }
+  if (oz == 0 || oy == 0 || ox == 0) return B2_OK;
+  std::lock_guard<std::mutex> lock(g_mu);
+  DeviceCtx* c = nullptr;
+  int rc = get_ctx(device, &c);
+  if (rc) return rc;
+  const size_t es = elem_size(src_dtype);
+  const int64_t pitch = (Xo + 3) / 4 * 4;  // elements; 16-byte aligned rows
+  const size_t in_bytes = static_cast<size_t>(Zi) * Yi * Xi * es;
+  const size_t mid_bytes = static_cast<size_t>(Zavg) * Yo * pitch * sizeof(float);
+  const size_t plane_out = static_cast<size_t>(oy) * ox * sizeof(float);
+  if ((rc = grow_device(&c->d_src, &c->d_src_bytes, in_bytes))) return rc;
+  if ((rc = grow_device(&c->d_mid, &c->d_mid_bytes, mid_bytes))) return rc;
+  if ((rc = grow_device(&c->d_dst, &c->d_dst_bytes, static_cast<size_t>(oz) * plane_out))) return rc;
+  void* d_src = c->d_src;
+  float* d_mid = static_cast<float*>(c->d_mid);
+  float* d_dst = static_cast<float*>(c->d_dst);
+
+  // need[z]: the last deskewed plane output plane z reads (+2: upper tap and a clamped neighbour)
+  const int64_t c0[3] = {crop_start ? crop_start[0] : 0, crop_start ? crop_start[1] : 0,
+                         crop_start ? crop_start[2] : 0};
+  std::vector<double> M(M12, M12 + 12);
+  std::vector<int64_t> need(static_cast<size_t>(oz));
+  int64_t run_max = -1;
+  for (int64_t z = 0; z < oz; ++z) {
+    double hi = -1e300;
+    for (int k = 0; k < 4; ++k) {
+      const double y = static_cast<double>((k & 1 ? oy - 1 : 0) + c0[1]);
+      const double x = static_cast<double>((k & 2 ? ox - 1 : 0) + c0[2]);
+      hi = std::max(hi, M[3] + static_cast<double>(z + c0[0]) * M[0] + y * M[1] + x * M[2]);
+    }
+    int64_t p = static_cast<int64_t>(std::floor(std::min(std::max(hi, -1.0e15), 1.0e15))) + 2;
+    p = std::min<int64_t>(std::max<int64_t>(p, -1), Zavg - 1);
+    run_max = std::max(run_max, p);  // planes are released in order: prefix maximum
+    need[static_cast<size_t>(z)] = run_max;
+  }
+
+  const size_t slice_bytes = static_cast<size_t>(Yo) * pitch * sizeof(float);
+  const int64_t per_slab = std::max<int64_t>(1, static_cast<int64_t>(kSlabBytes / slice_bytes));
+  const size_t row_bytes = static_cast<size_t>(Xi) * es;
+  std::vector<Slab> slabs;
+  int64_t zdone = 0;
+  for (int64_t a0 = 0; a0 < Zavg; a0 += per_slab) {
+    const int64_t cnt = std::min(per_slab, Zavg - a0);
+    const int64_t a1 = a0 + cnt;
+    const int64_t iy_hi = Yi - 1 - a0 * N;
+    const int64_t iy_lo = Yi - std::min<int64_t>(a1 * N, Yi);
+    Slab s;
+    Band b;
+    b.off = static_cast<size_t>(iy_lo) * row_bytes;
+    b.pitch = static_cast<size_t>(Yi) * row_bytes;
+    b.width = static_cast<size_t>(iy_hi - iy_lo + 1) * row_bytes;
+    b.rows = static_cast<size_t>(Zi);
+    s.bands.push_back(b);
+    // output planes whose deskewed source planes are complete after this slab
+    int64_t znext = zdone;
+    while (znext < oz && (need[static_cast<size_t>(znext)] < a1 || a1 == Zavg)) ++znext;
+    const int64_t z0 = zdone, zc = znext - zdone;
+    zdone = znext;
+    s.out_off = static_cast<size_t>(z0) * plane_out;
+    s.out_bytes = static_cast<size_t>(zc) * plane_out;
+    s.launch = [=](cudaStream_t st) {
+      const int slab[4] = {0, static_cast<int>(Yi), static_cast<int>(a0), static_cast<int>(cnt)};
+      int r = deskew_device(d_src, src_dtype, Zi, Yi, Xi, d_mid + a0 * Yo * pitch, Zavg, Yo, Xo,
+                            Zo_full, N, px32, pxct32, off32, B2_PATH_AUTO, st, slab, pitch);
+      if (r || zc == 0) return r;
+      const int64_t crop[3] = {c0[0] + z0, c0[1], c0[2]};
+      return affine_device(d_mid, B2_DTYPE_F32, Zavg, Yo, Xo, d_dst + z0 * oy * ox, zc, oy, ox,
+                           M.data(), crop, order, boundary, scrub, B2_PATH_AUTO, st, pitch, 0);
+    };
+    slabs.push_back(std::move(s));
+  }
+  return run_pipeline(*c, static_cast<const char*>(h_src), reinterpret_cast<char*>(h_dst), slabs);
+}
+
 // Flat-field correction with host buffers.  Phase 1: Y-bands of the source (all Z planes of a
 // range of rows: one strided cudaMemcpy2DAsync each) are uploaded while the medians of the
 // previous band are computed.  The pattern mean needs every median, so phase 2 starts after
@@ -568,6 +667,7 @@ int host_release() {
     if (c.d_src) cudaFree(c.d_src);
     if (c.d_dst) cudaFree(c.d_dst);
     if (c.d_ws) cudaFree(c.d_ws);
+    if (c.d_mid) cudaFree(c.d_mid);
     for (int r = 0; r < kRing; ++r) {
       if (c.h_in[r]) cudaFreeHost(c.h_in[r]);
       if (c.h_out[r]) cudaFreeHost(c.h_out[r]);

@@ -47,13 +47,34 @@ def deskew_then_register(raw, matrix, output_shape_zyx, *, ls_angle_deg, px_to_s
     import torch
 
     order = _interpolation_order(interpolation)
-    on_device = is_torch_tensor(raw)
-    src = raw if on_device else _to_device(raw, device)
-    mid = fast_deskew_zyx(src, ls_angle_deg, px_to_scan_ratio, keep_overhang, average_n_slices,
-                          row_align=4)
-    res = affine_warp(mid, matrix, output_shape_zyx, order=order, boundary="itk",
-                      crop_output_slicing=crop_output_slicing)
-    return res if on_device else _to_host(res, out)
+    if is_torch_tensor(raw):
+        mid = fast_deskew_zyx(raw, ls_angle_deg, px_to_scan_ratio, keep_overhang, average_n_slices,
+                              row_align=4)
+        return affine_warp(mid, matrix, output_shape_zyx, order=order, boundary="itk",
+                           crop_output_slicing=crop_output_slicing)
+    # host arrays: ONE pipelined C-ABI call (b2h_deskew_affine3d) — upload of the next tilt-row
+    # band, deskew, warp of the output planes whose source planes are complete and their
+    # download all overlap
+    import ctypes
+
+    from . import _cabi
+    from ._device import host_source
+    from .deskew import deskew_scalars
+    from .register import _crop_box
+
+    src, code = host_source(raw)
+    if src.ndim != 3:
+        raise ValueError("raw data must have ndim == 3 (Z, Y, X)")
+    s = deskew_scalars(src.shape, ls_angle_deg, px_to_scan_ratio, keep_overhang, average_n_slices)
+    starts, sizes = _crop_box(output_shape_zyx, crop_output_slicing)
+    out = check_out(out, sizes)
+    if out.size:
+        _cabi.check(_cabi.lib().b2h_deskew_affine3d(
+            src.ctypes.data_as(ctypes.c_void_p), code, s["Zi"], s["Yi"], s["Xi"], s["Zavg"], s["Yo"],
+            s["Xo"], s["Zo"], s["N"], s["px32"], s["pxct32"], s["off32"],
+            out.ctypes.data_as(ctypes.c_void_p), *sizes, _cabi.matrix12(matrix),
+            _cabi.int64x3(starts), int(order), _cabi.BOUNDARY_ITK, 1, resolve_device(device)))
+    return out
 
 
 def flatfield_then_deskew(raw, *, ls_angle_deg, px_to_scan_ratio, keep_overhang,

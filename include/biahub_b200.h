@@ -137,6 +137,19 @@ B2_API int b2h_affine3d(const void* h_src, int src_dtype, int64_t sz, int64_t sy
                  int order, int boundary, int scrub_nonfinite, int device);
 
 /*
+ * Chained unit of BASELINE configs[4]: deskew, then warp the deskewed float32 volume — the
+ * reference runs `biahub deskew` then `biahub register` with a zarr round trip in between
+ * (biahub/deskew.py:739-748, biahub/register.py:561-572).  The deskewed volume stays on the device;
+ * upload, both kernels and the download of finished output planes overlap.  The matrix / output
+ * shape refer to the DESKEWED volume (Zavg, Yo, Xo) exactly as in b2h_affine3d.
+ */
+B2_API int b2h_deskew_affine3d(const void* h_src, int src_dtype, int64_t Zi, int64_t Yi, int64_t Xi,
+                        int64_t Zavg, int64_t Yo, int64_t Xo, int64_t Zo_full, int average_n_slices,
+                        float px32, float pxct32, float off32, float* h_dst, int64_t oz, int64_t oy,
+                        int64_t ox, const double* M12, const int64_t* crop_start, int order,
+                        int boundary, int scrub_nonfinite, int device);
+
+/*
  * Flat-field correction (reference biahub/flat_field.py:105-122 `flat_field_zyx`, :152-166
  * `_flat_field_czyx`; the pipeline stage before deskew): pattern = median over Z of every (y, x)
  * pixel, out = (double(src) / pattern) * mean(pattern), rounded to float32 (what the czyx adapter

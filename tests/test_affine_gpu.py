@@ -395,3 +395,46 @@ def test_generic_lanes_along_y_variant(order):
         if order == 0:
             assert torch.equal(got, affine_warp(t, M, out_shape, order=0, boundary=boundary,
                                                 _path=_cabi.PATH_GATHER))
+
+
+@pytest.mark.parametrize("mname", ["c3", "generic", "zflip"])
+def test_host_chain_pipeline_many_slabs(mname):
+    """b2h_deskew_affine3d over several deskew slabs: output plane ranges are warped and
+    downloaded as soon as their deskewed source planes exist.  Must equal the device chain (one
+    deskew launch + one warp launch): bit for bit for z-separable matrices (the z-marching kernel
+    does not depend on how the output is cut along z), to fp32 rounding for the brick kernel."""
+    import torch
+
+    import biahub_b200 as b2
+
+    rng = np.random.default_rng(44)
+    raw = rng.integers(0, 65536, size=(400, 120, 1024), dtype=np.uint16)
+    kw = dict(ls_angle_deg=30.0, px_to_scan_ratio=0.386, keep_overhang=False, average_n_slices=3)
+    t = torch.from_numpy(raw.view(np.int16)).cuda().view(torch.uint16)
+    mid_shape = tuple(b2.fast_deskew_zyx(t, 30.0, 0.386, False, 3).shape)   # (40, 1024, 933)
+    assert mid_shape[0] * mid_shape[1] * mid_shape[2] * 4 > 3 * (48 << 20)   # >= 4 slabs
+    M = ao.register_matrix_c3(mid_shape)
+    if mname == "generic":
+        c = (np.array(mid_shape) - 1) / 2.0
+        a = np.radians(0.8)
+        R = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]])
+        tilt = np.eye(4)
+        tilt[:3, :3] = R
+        tilt[:3, 3] = c - R @ c
+        M = M @ tilt
+    elif mname == "zflip":
+        F = np.eye(4)
+        F[0, 0] = -1.0
+        F[0, 3] = mid_shape[0] - 1
+        M = F @ M
+    out_shape = (mid_shape[0] + 3, mid_shape[1] - 10, mid_shape[2] + 7)
+    dev = b2.deskew_then_register(t, M, out_shape, **kw).cpu().numpy()
+    host = b2.deskew_then_register(raw, M, out_shape, **kw)
+    assert host.shape == out_shape and host.dtype == np.float32
+    if mname == "c3":
+        assert np.array_equal(host, dev)
+    else:
+        assert np.abs(host - dev).max() <= 2e-5 * 65535.0
+    crop = (slice(3, 30), slice(5, 900), slice(10, 800))
+    hc = b2.deskew_then_register(raw, M, out_shape, crop_output_slicing=crop, **kw)
+    assert np.abs(hc - dev[crop]).max() <= (0 if mname == "c3" else 2e-5 * 65535.0)
