@@ -2,13 +2,17 @@
 import os, subprocess, sys, json
 CONFIGS = {
   "default plan":         dict(),
-  "A reg y128":           dict(B2_DESKEW_TX="128", B2_DESKEW_STAGE="0", B2_DESKEW_XFAST="0"),
-  "B reg x256":           dict(B2_DESKEW_TX="256", B2_DESKEW_STAGE="0", B2_DESKEW_XFAST="1"),
-  "C reg x128":           dict(B2_DESKEW_TX="128", B2_DESKEW_STAGE="0", B2_DESKEW_XFAST="1"),
-  "D reg y256":           dict(B2_DESKEW_TX="256", B2_DESKEW_STAGE="0", B2_DESKEW_XFAST="0"),
-  "E stage x256":         dict(B2_DESKEW_TX="256", B2_DESKEW_STAGE="1", B2_DESKEW_XFAST="1"),
-  "F stage x128":         dict(B2_DESKEW_TX="128", B2_DESKEW_STAGE="1", B2_DESKEW_XFAST="1"),
+  "L2 prefetch 592":      dict(B2_DESKEW_PREFETCH="592"),
 }
+if len(sys.argv) > 1 and sys.argv[1] == "full":
+    CONFIGS.update({
+      "A reg y128":           dict(B2_DESKEW_TX="128", B2_DESKEW_STAGE="0", B2_DESKEW_XFAST="0"),
+      "B reg x256":           dict(B2_DESKEW_TX="256", B2_DESKEW_STAGE="0", B2_DESKEW_XFAST="1"),
+      "C reg x128":           dict(B2_DESKEW_TX="128", B2_DESKEW_STAGE="0", B2_DESKEW_XFAST="1"),
+      "D reg y256":           dict(B2_DESKEW_TX="256", B2_DESKEW_STAGE="0", B2_DESKEW_XFAST="0"),
+      "E stage x256":         dict(B2_DESKEW_TX="256", B2_DESKEW_STAGE="1", B2_DESKEW_XFAST="1"),
+      "F stage x128":         dict(B2_DESKEW_TX="128", B2_DESKEW_STAGE="1", B2_DESKEW_XFAST="1"),
+    })
 INNER = r'''
 import sys; sys.path.insert(0, "/root/repo")
 import torch, json, biahub_b200 as b2
