@@ -27,13 +27,8 @@
 
 namespace b2 {
 
-constexpr int kFfThreads = 128;
+constexpr int kFfThreads = 256;
 constexpr int kFfPix = 4;  // pixels per thread (one 8-byte load per plane)
-constexpr int kFfBatch = 4;  // planes fetched ahead of the histogram updates
-// 9 CTAs x 128 threads per SM (<= 56 registers, 16 KB of counters each): the mantis plane
-// (614400 pixels = 153600 threads) then fits in ONE wave of 148 x 1152 thread slots; with 64
-// registers (1024 threads per SM) it needs a second, nearly empty wave that doubles the time
-constexpr int kFfMedianCtasPerSm = 9;
 
 struct FlatfieldParams {
   const uint16_t* src;
@@ -51,9 +46,9 @@ __device__ __forceinline__ uint32_t ff_slot(uint32_t bin, uint32_t j, uint32_t t
   return ((bin * kFfPix + j) * kFfThreads + t) * 2u;
 }
 
-__global__ void __launch_bounds__(kFfThreads, kFfMedianCtasPerSm)
+__global__ void __launch_bounds__(kFfThreads)
     flatfield_median_kernel(const __grid_constant__ FlatfieldParams p) {
-  __shared__ uint16_t hist[16 * kFfPix * kFfThreads];  // 16 KB
+  __shared__ uint16_t hist[16 * kFfPix * kFfThreads];  // 32 KB
   __shared__ unsigned long long block_sum;
   const uint32_t t = threadIdx.x;
   const uint32_t hbase = smem_u32(hist);
@@ -91,29 +86,19 @@ __global__ void __launch_bounds__(kFfThreads, kFfMedianCtasPerSm)
       for (uint32_t j = 0; j < kFfPix; ++j)
         asm volatile("st.shared.u16 [%0], %1;" ::"r"(hbase + ff_slot(b, j, t)), "h"((unsigned short)0));
     if (npx > 0) {
-      // kFfBatch planes are fetched before any of them is binned (the shared-memory updates are
-      // ordered, so the loads would otherwise issue one per iteration).  Measured: 2.4 ms per
-      // mantis volume with or without the batch — the kernel sits at 25 % of the DRAM bandwidth
-      // with 256-byte requests spread over all Z planes; it is 4 % of the PCIe-bound end-to-end
-      // time and was left there.
-      for (int zb = 0; zb < p.Z; zb += kFfBatch) {
-        uint32_t v[kFfBatch][kFfPix];
+#pragma unroll 4
+      for (int z = 0; z < p.Z; ++z) {
+        uint32_t v[kFfPix];
+        load4(z, v);
 #pragma unroll
-        for (int b = 0; b < kFfBatch; ++b)
-          if (zb + b < p.Z) load4(zb + b, v[b]);
-#pragma unroll
-        for (int b = 0; b < kFfBatch; ++b) {
-          if (zb + b >= p.Z) break;
-#pragma unroll
-          for (uint32_t j = 0; j < kFfPix; ++j) {
-            const uint32_t hi = pass == 0 ? 0u : (v[b][j] >> (shift + 4));
-            if (hi == prefix[j]) {
-              const uint32_t a = hbase + ff_slot((v[b][j] >> shift) & 15u, j, t);
-              unsigned short c;
-              asm volatile("ld.shared.u16 %0, [%1];" : "=h"(c) : "r"(a));
-              c = static_cast<unsigned short>(c + 1);
-              asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"(c));
-            }
+        for (uint32_t j = 0; j < kFfPix; ++j) {
+          const uint32_t hi = pass == 0 ? 0u : (v[j] >> (shift + 4));
+          if (hi == prefix[j]) {
+            const uint32_t a = hbase + ff_slot((v[j] >> shift) & 15u, j, t);
+            unsigned short c;
+            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(c) : "r"(a));
+            c = static_cast<unsigned short>(c + 1);
+            asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"(c));
           }
         }
       }
@@ -156,7 +141,6 @@ __global__ void __launch_bounds__(kFfThreads, kFfMedianCtasPerSm)
     }
   }
   if (need_next) {
-#pragma unroll 8
     for (int z = 0; z < p.Z; ++z) {
       uint32_t v[kFfPix];
       load4(z, v);
@@ -219,44 +203,35 @@ __global__ void __launch_bounds__(kFfThreads)
   const int zb = p.z0 + blockIdx.y * planes_per_cta;
   const int ze = min(zb + planes_per_cta, p.z0 + p.zn);
   OUT* __restrict__ dst = static_cast<OUT*>(p.dst);
-  constexpr int kB = 4;  // planes fetched before the float64 chains start
-  for (int z0 = zb; z0 < ze; z0 += kB) {
-    uint32_t v[kB][kFfPix];
+#pragma unroll 2
+  for (int z = zb; z < ze; ++z) {
+    const int64_t off = static_cast<int64_t>(z) * p.P + pix;
+    uint32_t v[kFfPix];
+    if (vec) {
+      const uint2 w = __ldg(reinterpret_cast<const uint2*>(p.src + off));
+      v[0] = w.x & 0xffffu; v[1] = w.x >> 16; v[2] = w.y & 0xffffu; v[3] = w.y >> 16;
+    } else {
 #pragma unroll
-    for (int b = 0; b < kB; ++b) {
-      if (z0 + b >= ze) break;
-      const int64_t off = static_cast<int64_t>(z0 + b) * p.P + pix;
-      if (vec) {
-        const uint2 w = __ldcs(reinterpret_cast<const uint2*>(p.src + off));
-        v[b][0] = w.x & 0xffffu; v[b][1] = w.x >> 16; v[b][2] = w.y & 0xffffu; v[b][3] = w.y >> 16;
-      } else {
-#pragma unroll
-        for (int j = 0; j < kFfPix; ++j) v[b][j] = j < npx ? __ldg(p.src + off + j) : 0u;
-      }
+      for (int j = 0; j < kFfPix; ++j) v[j] = j < npx ? __ldg(p.src + off + j) : 0u;
     }
+    double r[kFfPix];
 #pragma unroll
-    for (int b = 0; b < kB; ++b) {
-      if (z0 + b >= ze) break;
-      const int64_t off = static_cast<int64_t>(z0 + b) * p.P + pix;
-      double r[kFfPix];
-#pragma unroll
-      for (int j = 0; j < kFfPix; ++j) r[j] = ff_value(v[b][j], pat[j], rcp[j], mean, plain[j]);
-      if (sizeof(OUT) == 4) {
-        float* o = reinterpret_cast<float*>(dst) + off;
-        if (vec) {
-          st_global_cs4(o, make_float4(__double2float_rn(r[0]), __double2float_rn(r[1]),
-                                       __double2float_rn(r[2]), __double2float_rn(r[3])));
-        } else {
-#pragma unroll
-          for (int j = 0; j < kFfPix; ++j)
-            if (j < npx) o[j] = __double2float_rn(r[j]);
-        }
+    for (int j = 0; j < kFfPix; ++j) r[j] = ff_value(v[j], pat[j], rcp[j], mean, plain[j]);
+    if (sizeof(OUT) == 4) {
+      float* o = reinterpret_cast<float*>(dst) + off;
+      if (vec) {
+        st_global_cs4(o, make_float4(__double2float_rn(r[0]), __double2float_rn(r[1]),
+                                     __double2float_rn(r[2]), __double2float_rn(r[3])));
       } else {
-        double* o = reinterpret_cast<double*>(dst) + off;
 #pragma unroll
         for (int j = 0; j < kFfPix; ++j)
-          if (j < npx) __stcs(o + j, r[j]);
+          if (j < npx) o[j] = __double2float_rn(r[j]);
       }
+    } else {
+      double* o = reinterpret_cast<double*>(dst) + off;
+#pragma unroll
+      for (int j = 0; j < kFfPix; ++j)
+        if (j < npx) __stcs(o + j, r[j]);
     }
   }
 }
