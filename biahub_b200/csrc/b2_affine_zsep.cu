@@ -14,13 +14,15 @@
 // along z (2 FMA).  The per-z tap table (plane indices + weights) is computed once per CTA into
 // shared memory.  Every source plane brick is read from global memory exactly once per CTA and
 // every output voxel is written once, coalesced along x.
+//
+// m00 == 1 (all of the reference's builder matrices and stabilisation shifts) takes the "regular
+// run": each arriving plane finishes one output plane (o = fma(w1, v, pend)) and starts the next
+// (pend = w0 * v) — same operations and order as the general two-plane blend, bit-identical, 25 %
+// fewer instructions.  The ring is 6-8 planes deep (chosen per launch from the plane brick size).
 #include "b2_affine.cuh"
 
 namespace b2 {
 
-#ifndef B2_ZSEP_MAXREG
-#define B2_ZSEP_MAXREG 72  // 3 CTAs (27 warps) per SM
-#endif
 // Output tile: 16 x 64 points (y x x), lanes along x.  LY variant (matrices that map output y
 // onto source x, e.g. the 90-degree rotations of the manual registration): 64 x 16, lanes along
 // y, so that a warp's taps run along a brick ROW (conflict-free shared-memory reads; with lanes
