@@ -70,7 +70,7 @@ def build(force: bool = False, verbose: bool = False, extra_flags=()) -> str:
     for src in sources():
         obj = os.path.join(obj_dir, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
-        env_extra = os.environ.get("B2_NVCC_EXTRA", "").split()  # e.g. -DB2_ZSEP_MAXREG=56 for sweeps
+        env_extra = os.environ.get("B2_NVCC_EXTRA", "").split()  # extra nvcc flags for sweeps, e.g. -DB2_STORE_CG
         cmd = [nvcc, *NVCC_FLAGS, *extra_flags, *env_extra, "-I", INCLUDE, "-c", src, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas")
