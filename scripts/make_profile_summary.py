@@ -34,8 +34,11 @@ def full(wl):
 
 def sass():
     out = ["# SASS evidence (cuobjdump -sass of the built objects): mnemonic counts per kernel family"]
-    for obj, pat in (("b2_deskew.o", "deskew_tma_kernelItLi3ELi128"), ("b2_deskew.o", "deskew_stage_kernelILi1ELi256"),
-                     ("b2_affine_zsep.o", "affine_zsep_kernelIfLi1ELi1ELb1"), ("b2_affine_brick.o", "affine_brick_kernelIfLi1ELi1ELb1")):
+    for obj, pat in (("b2_deskew.o", "deskew_tma_kernelItLi3ELi256"), ("b2_deskew.o", "deskew_stage_kernelILi1ELi256"),
+                     ("b2_affine_zsep.o", "affine_zsep_kernelIfLi1ELi1ELb1ELb0"), ("b2_affine_zsep.o", "affine_zsep_kernelIfLi1ELi1ELb1ELb1"),
+                     ("b2_affine_brick.o", "affine_brick_kernelIfLi1ELi1ELb1ELb0"),
+                     ("b2_flatfield.o", "flatfield_median_kernel"), ("b2_flatfield.o", "flatfield_apply_kernelIf"),
+                     ("b2_fill.o", "fill_bits_kernel"), ("b2_fill.o", "fill_dilate_z_kernelILb1")):
         p = os.path.join(ROOT, "biahub_b200", "_lib", "obj", obj)
         txt = subprocess.run(["cuobjdump", "-sass", p], capture_output=True, text=True).stdout
         m = re.search(r"Function : (\S*%s\S*)(.*?)(?=Function :|\Z)" % pat, txt, re.S)
@@ -44,7 +47,7 @@ def sass():
         ops = re.findall(r"^\s+/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d\s+)?([A-Z0-9_.]+)", body, re.M)
         cnt = {}
         for o in ops: cnt[o] = cnt.get(o, 0) + 1
-        keys = [k for k in cnt if re.match(r"UTMALDG|UBLKCP|SYNCS|LDS|STG|LDG|TEX|TLD|PRMT|FFMA|FMUL|FADD|I2F|DFMA|DMUL|DADD", k)]
+        keys = [k for k in cnt if re.match(r"UTMALDG|UBLKCP|SYNCS|LDS|STS|STG|LDG|TEX|TLD|PRMT|FFMA|FMUL|FADD|I2F|DFMA|DMUL|DADD|VOTE|REDUX|SHF|BAR", k)]
         out.append(f"\n{m.group(1)}\n  total SASS instructions: {len(ops)}")
         for k in sorted(keys, key=lambda k: -cnt[k]): out.append(f"  {k:34s} {cnt[k]}")
         out.append("  texture instructions (TEX/TLD): %d" % sum(v for k, v in cnt.items() if k.startswith(("TEX", "TLD"))))
