@@ -42,6 +42,28 @@ def test_compute_fails_loudly_without_gpu():
         b2.apply_affine_transform(np.ones((4, 4, 4)), np.eye(4), (4, 4, 4))
     with pytest.raises(_cabi.B2Error):
         b2.apply_stabilization_transform(np.ones((4, 4, 4)), [np.eye(4)], 0)
+    u16 = np.ones((4, 4, 8), dtype=np.uint16)
+    with pytest.raises(_cabi.B2Error, match="no CPU fallback"):
+        b2.flat_field_zyx(u16)
+    with pytest.raises(_cabi.B2Error, match="no CPU fallback"):
+        b2._flat_field_czyx(u16[None], [0])
+    with pytest.raises(_cabi.B2Error, match="no CPU fallback"):
+        b2.deskew_then_register(raw, np.eye(4), (8, 8, 8), ls_angle_deg=30.0, px_to_scan_ratio=0.386,
+                                keep_overhang=True)
+
+
+def test_flat_field_host_logic_without_gpu():
+    """Argument handling that needs no device: dtype / rank errors, pass-through channels."""
+    with pytest.raises(NotImplementedError, match="uint16"):
+        b2.flat_field_zyx(np.ones((3, 4, 5), dtype=np.float32))
+    with pytest.raises(ValueError):
+        b2.flat_field_zyx(np.ones((4, 5), dtype=np.uint16))
+    with pytest.raises(ValueError):
+        b2._flat_field_czyx(np.ones((3, 4, 5), dtype=np.uint16), [0])
+    # no target channel: every channel is passed through as float32, nothing touches the device
+    czyx = np.arange(2 * 3 * 4 * 5, dtype=np.uint16).reshape(2, 3, 4, 5)
+    out = b2._flat_field_czyx(czyx, [])
+    assert out.dtype == np.float32 and np.array_equal(out, czyx.astype(np.float32))
 
 
 def test_product_package_never_imports_oracle():
