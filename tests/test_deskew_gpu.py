@@ -180,3 +180,31 @@ def test_library_is_the_compute_path():
     b2._fast_deskew_czyx(raw[None], ls_angle_deg=30.0, px_to_scan_ratio=0.386,
                          keep_overhang=False, average_n_slices=3)
     assert _cabi.launch_count() > before
+
+
+@pytest.mark.parametrize("dtype,X", [("uint16", 132), ("uint16", 203), ("float32", 130), ("float32", 67)])
+@pytest.mark.parametrize("n", [1, 3, 4])
+def test_unaligned_rows_take_the_brick_kernel_with_manual_fill(dtype, X, n):
+    """Source rows that are not 16-byte aligned cannot be addressed by TMA: the register kernel
+    then fills its brick with coalesced element loads (same swizzled layout, same arithmetic).
+    Bit-identical to the plain gather kernel and to the oracle; PATH_TMA still refuses."""
+    import torch
+
+    import biahub_b200 as b2
+    from biahub_b200 import _cabi
+
+    rng = np.random.default_rng(91)
+    shape = (150, 26, X)
+    raw = (rng.integers(0, 65536, size=shape, dtype=np.uint16) if dtype == "uint16"
+           else (rng.random(shape, dtype=np.float32) * 4095).astype(np.float32))
+    assert (X * raw.itemsize) % 16 != 0
+    t = _to_cuda(raw)
+    for keep in (False, True):
+        auto = b2.fast_deskew_zyx(t, 30.0, 0.386, keep, n)
+        gather = b2.fast_deskew_zyx(t, 30.0, 0.386, keep, n, _path=_cabi.PATH_GATHER)
+        assert torch.equal(auto, gather)
+        want = do.deskew_oracle_numpy(raw, 30.0, 0.386, keep, n)
+        rngv = 65535.0 if dtype == "uint16" else 4095.0
+        assert np.abs(auto.cpu().numpy() - want).max() <= 2e-7 * rngv
+    with pytest.raises(_cabi.B2Unsupported):
+        b2.fast_deskew_zyx(t, 30.0, 0.386, False, n, _path=_cabi.PATH_TMA)
