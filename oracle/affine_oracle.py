@@ -36,10 +36,13 @@ FLT_MAX = float(np.finfo(np.float32).max)
 
 
 def scrub_nonfinite(vol):
-    """``np.nan_to_num(x, nan=0)`` then float32 — reference biahub/register.py:254, 266;
-    biahub/stabilize.py:84-85.  NaN→0, +inf→FLT_MAX, −inf→−FLT_MAX (after the float32 cast
-    float64 maxima would overflow, so the scrub is applied in the input dtype like numpy does,
-    then re-applied after the cast for float64 inputs whose maxima exceed float32)."""
+    """``np.nan_to_num(x, nan=0)`` in the INPUT dtype, then ``astype(float32)`` — the reference's
+    order (biahub/register.py:254, 266; biahub/stabilize.py:84-85).  NaN→0, +inf→max, −inf→−max
+    of the input dtype.  For float32 inputs that is ±FLT_MAX.  For float64 inputs the cast comes
+    AFTER the scrub, so ±inf (scrubbed to ±DBL_MAX) and finite magnitudes beyond FLT_MAX reach
+    the resampler as float32 ±inf: this function returns them as such.  What ITK then does with
+    an infinite tap is unpinned; ``affine_oracle_numpy`` (and the CUDA path) scrub once more at
+    the tap, i.e. treat them as ±FLT_MAX (golden case ``f64_overflow``)."""
     vol = np.nan_to_num(np.asarray(vol), nan=0)
     with np.errstate(over="ignore"):
         vol = vol.astype(_f32)
@@ -95,7 +98,7 @@ def affine_oracle_numpy(vol, matrix, output_shape_zyx, order=1, boundary="consta
     """
     if boundary not in ("constant", "itk"):
         raise ValueError(boundary)
-    src = scrub_nonfinite(vol).astype(np.float64)
+    src = np.nan_to_num(scrub_nonfinite(vol), nan=0).astype(np.float64)  # tap scrub, see above
     M = np.asarray(matrix, dtype=np.float64)
     A, t = M[:3, :3], M[:3, 3]
     n = src.shape
@@ -212,7 +215,7 @@ def affine_oracle_points(vol, matrix, points, order=1, boundary="constant"):
             inside &= (c[d] >= -0.5) & (c[d] < n[d] - 0.5)
 
     def tap(iz, iy, ix):
-        return scrub_nonfinite(src[iz, iy, ix]).astype(np.float64)
+        return np.nan_to_num(scrub_nonfinite(src[iz, iy, ix]), nan=0).astype(np.float64)
 
     if order == 0:
         idx = [np.clip(np.floor(c[d] + 0.5).astype(np.int64), 0, n[d] - 1) for d in range(3)]
@@ -238,3 +241,138 @@ def affine_oracle_points(vol, matrix, points, order=1, boundary="constant"):
                                nxt[2] if dx else base[2]) * (wz * wy * wx)
     with np.errstate(over="ignore"):
         return np.where(inside, val, 0.0).astype(_f32)
+
+
+# ---- method="scipy": cubic B-spline, scipy ``mode="constant"`` (reference register.py:271-272) ----
+SPLINE3_POLE = float(np.sqrt(3.0) - 2.0)
+
+
+def spline3_prefilter_numpy(vol):
+    """``scipy.ndimage.spline_filter(vol, 3, output=float64, mode="constant")`` restated: per
+    axis (length > 1) scale by (1-z)(1-1/z) = 6, causal pass ``c[i] += z c[i-1]`` started from
+    the mirror-extended sum ``c[0] = sum_k z^k s[mirror(k)]``, anti-causal pass
+    ``c[i] = z (c[i+1] - c[i])`` started from ``c[n-1] = z/(z^2-1) (z c[n-2] + c[n-1])``; scipy
+    uses the MIRROR initialisation for ``mode="constant"`` (probed on scipy 1.18.1: identical
+    bits to ``mode="mirror"``).  Pinned to scipy ≤ 1e-15 relative in tests/test_affine_reference.py."""
+    c = np.asarray(vol, dtype=np.float64).copy()
+    z = SPLINE3_POLE
+    for axis in range(c.ndim):
+        n = c.shape[axis]
+        if n < 2:
+            continue
+        c = np.moveaxis(c, axis, 0)
+        c *= (1.0 - z) * (1.0 - 1.0 / z)
+        k = np.arange(64)  # z^64 ~ 3e-37: the infinite mirror sum to double precision
+        idx = k % (2 * n - 2)
+        idx = np.where(idx >= n, 2 * n - 2 - idx, idx)
+        c[0] = np.tensordot(z ** k, c[idx], axes=(0, 0))
+        for i in range(1, n):
+            c[i] += z * c[i - 1]
+        c[n - 1] = (z / (z * z - 1.0)) * (z * c[n - 2] + c[n - 1])
+        for i in range(n - 2, -1, -1):
+            c[i] = z * (c[i + 1] - c[i])
+        c = np.moveaxis(c, 0, axis)
+    return c
+
+
+def _bspline3_weights(t):
+    return ((1 - t) ** 3 / 6, (3 * t ** 3 - 6 * t ** 2 + 4) / 6,
+            (-3 * t ** 3 + 3 * t ** 2 + 3 * t + 1) / 6, t ** 3 / 6)
+
+
+def _round_like_scipy(val, dtype):
+    """Output conversion of scipy's NI_GeometricTransform: floats cast; unsigned
+    ``t > 0 ? t + 0.5 : 0`` clamped then truncated; signed ``t ± 0.5`` clamped then truncated."""
+    dtype = np.dtype(dtype)
+    if dtype.kind == "f":
+        with np.errstate(over="ignore"):
+            return val.astype(dtype)
+    info = np.iinfo(dtype)
+    if dtype.kind == "u":
+        t = np.where(val > 0, val + 0.5, 0.0)
+    else:
+        t = np.where(val > 0, val + 0.5, val - 0.5)
+    return np.trunc(np.clip(t, info.min, info.max)).astype(dtype)
+
+
+def affine_oracle_spline3(vol, matrix, crop_output_slicing=None, z_chunk=4):
+    """The reference's ``method="scipy"`` call ``scipy.ndimage.affine_transform(zyx, M, shape)``
+    restated: the third positional argument is scipy's ``offset`` (ignored for a homogeneous 4x4
+    matrix), so the output grid is ALWAYS the input's shape, order 3, ``mode="constant"``,
+    ``cval=0``, prefilter on, output dtype = input dtype.  Coordinates outside [0, n-1] → 0; the
+    4x4x4 taps ``floor(c)-1 … floor(c)+2`` are mirror-extended."""
+    vol = np.asarray(vol)
+    coef = spline3_prefilter_numpy(vol)
+    M = np.asarray(matrix, dtype=np.float64)
+    A, t = M[:3, :3], M[:3, 3]
+    n = vol.shape
+    start, size = _crop_box(n, crop_output_slicing)
+    out = np.zeros(size, dtype=vol.dtype)
+    if 0 in size:
+        return out
+
+    def mirror(i, nn):
+        if nn == 1:
+            return np.zeros_like(i)
+        p = 2 * nn - 2
+        i = np.mod(i, p)
+        return np.where(i >= nn, p - i, i)
+
+    ys = np.arange(start[1], start[1] + size[1], dtype=np.float64)[None, :, None]
+    xs = np.arange(start[2], start[2] + size[2], dtype=np.float64)[None, None, :]
+    for z0 in range(0, size[0], z_chunk):
+        z1 = min(z0 + z_chunk, size[0])
+        zs = np.arange(start[0] + z0, start[0] + z1, dtype=np.float64)[:, None, None]
+        c = [((t[d] + zs * A[d, 0]) + ys * A[d, 1]) + xs * A[d, 2] for d in range(3)]
+        inside = np.ones(c[0].shape, dtype=bool)
+        for d in range(3):
+            inside &= (c[d] >= 0.0) & (c[d] <= n[d] - 1)
+        fl = [np.floor(np.where(inside, c[d], 0.0)) for d in range(3)]
+        W = [_bspline3_weights(np.where(inside, c[d], 0.0) - fl[d]) for d in range(3)]
+        val = np.zeros(c[0].shape, dtype=np.float64)
+        for a0 in range(4):
+            iz = mirror(fl[0].astype(np.int64) - 1 + a0, n[0])
+            for a1 in range(4):
+                iy = mirror(fl[1].astype(np.int64) - 1 + a1, n[1])
+                for a2 in range(4):
+                    ix = mirror(fl[2].astype(np.int64) - 1 + a2, n[2])
+                    val += coef[iz, iy, ix] * (W[0][a0] * W[1][a1] * W[2][a2])
+        out[z0:z1] = _round_like_scipy(np.where(inside, val, 0.0), vol.dtype)
+    return out
+
+
+# ---- the reference's wrappers restated (register.py:202-281, stabilize.py:32-90) ----------
+_ANTS_ORDER = {"linear": 1, "nearestneighbor": 0}
+
+
+def apply_affine_transform_oracle(zyx_data, matrix, output_shape_zyx, method="ants",
+                                  interpolation="linear", crop_output_slicing=None):
+    """Restatement of the reference's ``apply_affine_transform`` with the ANTs call replaced by
+    the ITK-rule oracle.  Pinned against the reference function itself (run with the fake ants of
+    oracle/ref_loader.py) through tests/golden/golden_affine_v1.npz."""
+    zyx_data = np.asarray(zyx_data)
+    if zyx_data.ndim == 4:
+        _, size = _crop_box(output_shape_zyx, crop_output_slicing)
+        out = np.zeros((zyx_data.shape[0],) + size, dtype=_f32)
+        for c in range(zyx_data.shape[0]):
+            out[c] = apply_affine_transform_oracle(zyx_data[c], matrix, output_shape_zyx, method,
+                                                   interpolation, crop_output_slicing)
+        return out
+    if method == "ants":
+        return affine_oracle_numpy(zyx_data, matrix, output_shape_zyx, _ANTS_ORDER[interpolation],
+                                   "itk", crop_output_slicing)
+    if method == "scipy":
+        return affine_oracle_spline3(np.nan_to_num(zyx_data, nan=0), matrix, crop_output_slicing)
+    raise ValueError(f"Unknown method {method}")
+
+
+def apply_stabilization_oracle(zyx_data, list_of_shifts, input_time_index, output_shape=None):
+    """Restatement of the reference's ``apply_stabilization_transform`` (stabilize.py:32-90)."""
+    zyx_data = np.asarray(zyx_data)
+    if output_shape is None:
+        output_shape = zyx_data.shape[-3:]
+    M = np.asarray(list_of_shifts[input_time_index], dtype=np.float64)
+    if zyx_data.ndim == 4:
+        return np.stack([affine_oracle_numpy(zyx_data[c], M, output_shape, 1, "itk")
+                         for c in range(zyx_data.shape[0])]).astype(_f32)
+    return affine_oracle_numpy(zyx_data, M, output_shape, 1, "itk")

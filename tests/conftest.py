@@ -44,6 +44,20 @@ def golden():
 
 
 @pytest.fixture(scope="session")
+def golden_affine():
+    """Outputs of the reference's OWN register/stabilize functions (tests/golden/make_golden_affine.py)."""
+    import json
+
+    import numpy as np
+
+    here = os.path.join(ROOT, "tests", "golden")
+    arrays = np.load(os.path.join(here, "golden_affine_v1.npz"))
+    with open(os.path.join(here, "golden_affine_v1.json")) as fh:
+        meta = json.load(fh)
+    return arrays, meta
+
+
+@pytest.fixture(scope="session")
 def built_lib():
     from biahub_b200 import _build
 
