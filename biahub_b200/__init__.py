@@ -16,6 +16,7 @@ an importable ``biahub`` at these functions.
 from . import _cabi  # noqa: F401
 from .deskew import (  # noqa: F401
     _average_n_slices,
+    _average_n_slices_torch,
     _deskew_czyx,
     _fast_deskew_czyx,
     _get_averaged_shape,
@@ -35,6 +36,7 @@ from .register import (  # noqa: F401
     get_3D_rescaling_matrix,
     get_3D_rotation_matrix,
     rescale_voxel_size,
+    spline_warp,
 )
 from .flat_field import _flat_field_czyx, flat_field_correction, flat_field_zyx  # noqa: F401
 from .pipeline import deskew_then_register, flatfield_then_deskew  # noqa: F401

@@ -12,7 +12,7 @@ import threading
 
 import numpy as np
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 DTYPE_U16 = 0
 DTYPE_F32 = 1
@@ -35,6 +35,7 @@ EXPORTS = (
     "b2_affine3d", "b2_deskew_pitched", "b2_affine3d_pitched", "b2_overhang_fill_workspace", "b2_overhang_fill", "b2h_deskew",
     "b2h_affine3d", "b2h_release", "b2_launch_count",
     "b2_flatfield_workspace", "b2_flatfield_u16", "b2h_flatfield_u16", "b2h_deskew_affine3d",
+    "b2_overhang_fill_ex", "b2_average_slices", "b2h_deskew_fill", "b2_spline3_workspace", "b2_affine3d_spline3", "b2h_affine3d_spline3",
 )
 
 
@@ -100,6 +101,19 @@ def lib() -> ctypes.CDLL:
                                                _f32, _f32, _f32, _vp, _i64, _i64, _i64,
                                                ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_i64),
                                                _int, _int, _int, _int]
+        handle.b2_overhang_fill_ex.argtypes = [_vp, _i64, _i64, _i64, _int, _f32, _int, _int, _vp,
+                                               ctypes.c_size_t, _vp]
+        handle.b2_average_slices.argtypes = [_vp, _i64, _i64, _int, _vp, _vp]
+        handle.b2h_deskew_fill.argtypes = [_vp, _int, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _i64,
+                                           _int, _f32, _f32, _f32, _int, _f32, _int]
+        handle.b2_spline3_workspace.argtypes = [_i64, _i64, _i64]
+        handle.b2_spline3_workspace.restype = ctypes.c_size_t
+        handle.b2_affine3d_spline3.argtypes = [_vp, _int, _i64, _i64, _i64, _vp, _int, _i64, _i64,
+                                               _i64, ctypes.POINTER(ctypes.c_double),
+                                               ctypes.POINTER(_i64), _int, _vp, ctypes.c_size_t, _vp]
+        handle.b2h_affine3d_spline3.argtypes = [_vp, _int, _i64, _i64, _i64, _vp, _int, _i64, _i64,
+                                                _i64, ctypes.POINTER(ctypes.c_double),
+                                                ctypes.POINTER(_i64), _int, _int]
         handle.b2h_release.restype = _int
         handle.b2_launch_count.restype = ctypes.c_uint64
         if handle.b2_abi_version() != ABI_VERSION:

@@ -70,6 +70,22 @@ int host_deskew(const void* h_src, int src_dtype, int64_t Zi, int64_t Yi, int64_
 int host_affine(const void* h_src, int src_dtype, int64_t sz, int64_t sy, int64_t sx, float* h_dst,
                 int64_t oz, int64_t oy, int64_t ox, const double* M12, const int64_t* crop_start,
                 int order, int boundary, int scrub, int device);
+int host_deskew_fill(const void* h_src, int src_dtype, int64_t Zi, int64_t Yi, int64_t Xi,
+                     float* h_dst, int64_t Zavg, int64_t Yo, int64_t Xo, int64_t Zo_full, int N,
+                     float px32, float pxct32, float off32, int fill_mode, float fill_value,
+                     int device);
+size_t spline_workspace_bytes(int64_t sz, int64_t sy, int64_t sx);
+int affine_spline_device(const void* src, int src_dtype, int64_t sz, int64_t sy, int64_t sx,
+                         void* dst, int dst_dtype, int64_t oz, int64_t oy, int64_t ox,
+                         const double* M12, const int64_t* crop_start, int scrub, void* ws,
+                         size_t ws_bytes, cudaStream_t st);
+int host_affine_spline(const void* h_src, int src_dtype, int64_t sz, int64_t sy, int64_t sx,
+                       void* h_dst, int dst_dtype, int64_t oz, int64_t oy, int64_t ox,
+                       const double* M12, const int64_t* crop_start, int scrub, int device);
+int fill_device_ex(float* vol, int64_t z, int64_t y, int64_t x, int use_mean, float fill_value,
+                   int iterations, int connectivity, void* ws, size_t ws_bytes, cudaStream_t stream);
+int average_slices_device(const float* src, int64_t z, int64_t plane, int n, float* dst,
+                          cudaStream_t stream);
 int host_release();
 size_t flatfield_workspace_bytes(int64_t Y, int64_t X);
 int flatfield_begin(int64_t Y, int64_t X, void* ws, cudaStream_t stream);
@@ -231,6 +247,57 @@ int b2h_deskew_affine3d(const void* h_src, int src_dtype, int64_t Zi, int64_t Yi
   return b2::host_deskew_affine(h_src, src_dtype, Zi, Yi, Xi, Zavg, Yo, Xo, Zo_full,
                                 average_n_slices, px32, pxct32, off32, h_dst, oz, oy, ox, M12,
                                 crop_start, order, boundary, scrub_nonfinite, device);
+}
+
+int b2_overhang_fill_ex(float* vol, int64_t z, int64_t y, int64_t x, int use_mean, float fill_value,
+                        int iterations, int connectivity, void* workspace, size_t workspace_bytes,
+                        void* stream) {
+  int rc = b2::require_device();
+  if (rc) return rc;
+  return b2::fill_device_ex(vol, z, y, x, use_mean, fill_value, iterations, connectivity, workspace,
+                            workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int b2_average_slices(const float* src, int64_t z, int64_t plane_elems, int n, float* dst,
+                      void* stream) {
+  int rc = b2::require_device();
+  if (rc) return rc;
+  return b2::average_slices_device(src, z, plane_elems, n, dst, static_cast<cudaStream_t>(stream));
+}
+
+int b2h_deskew_fill(const void* h_src, int src_dtype, int64_t Zi, int64_t Yi, int64_t Xi,
+                    float* h_dst, int64_t Zavg, int64_t Yo, int64_t Xo, int64_t Zo_full,
+                    int average_n_slices, float px32, float pxct32, float off32, int fill_mode,
+                    float fill_value, int device) {
+  int rc = b2::require_device();
+  if (rc) return rc;
+  return b2::host_deskew_fill(h_src, src_dtype, Zi, Yi, Xi, h_dst, Zavg, Yo, Xo, Zo_full,
+                              average_n_slices, px32, pxct32, off32, fill_mode, fill_value, device);
+}
+
+size_t b2_spline3_workspace(int64_t sz, int64_t sy, int64_t sx) {
+  return b2::spline_workspace_bytes(sz, sy, sx);
+}
+
+int b2_affine3d_spline3(const void* src, int src_dtype, int64_t sz, int64_t sy, int64_t sx,
+                        void* dst, int dst_dtype, int64_t oz, int64_t oy, int64_t ox,
+                        const double* M12, const int64_t* crop_start, int scrub_nonfinite,
+                        void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = b2::require_device();
+  if (rc) return rc;
+  return b2::affine_spline_device(src, src_dtype, sz, sy, sx, dst, dst_dtype, oz, oy, ox, M12,
+                                  crop_start, scrub_nonfinite, workspace, workspace_bytes,
+                                  static_cast<cudaStream_t>(stream));
+}
+
+int b2h_affine3d_spline3(const void* h_src, int src_dtype, int64_t sz, int64_t sy, int64_t sx,
+                         void* h_dst, int dst_dtype, int64_t oz, int64_t oy, int64_t ox,
+                         const double* M12, const int64_t* crop_start, int scrub_nonfinite,
+                         int device) {
+  int rc = b2::require_device();
+  if (rc) return rc;
+  return b2::host_affine_spline(h_src, src_dtype, sz, sy, sx, h_dst, dst_dtype, oz, oy, ox, M12,
+                                crop_start, scrub_nonfinite, device);
 }
 
 int b2h_release(void) { return b2::host_release(); }

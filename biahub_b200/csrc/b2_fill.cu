@@ -13,6 +13,9 @@
 // HBM traffic: the volume is read in A and C and written only where masked; the words are 3 % of
 // it.  (The first version made four byte-per-voxel passes with 7-tap loops: 13.8 ms on the
 // mantis keep_overhang volume; this one: see DESIGN.md.)
+#include <algorithm>
+#include <utility>
+
 #include "b2_common.cuh"
 
 namespace b2 {
@@ -195,14 +198,87 @@ __global__ void __launch_bounds__(kFillThreads)
   }
 }
 
+// One iteration of scipy.ndimage.binary_dilation with its default structuring element (the 3-D
+// cross, 6-connectivity; border_value 0) on the bit words — the numpy variant of the fill used by
+// the legacy `deskew_zyx` (reference biahub/deskew.py:277-336, `_fill_overhang_with_mean`).
+__global__ void __launch_bounds__(kFillThreads)
+    fill_dilate_cross_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int W, int X,
+                             int Y, int Z, int64_t rows) {
+  const int64_t plane_words = static_cast<int64_t>(Y) * W;
+  const uint32_t tail = (X & 31) ? ((1u << (X & 31)) - 1u) : 0xffffffffu;  // valid bits of the last word
+  for (int64_t row = static_cast<int64_t>(blockIdx.x) * kFillRowsPerCta;
+       row < rows && row < (static_cast<int64_t>(blockIdx.x) + 1) * kFillRowsPerCta; ++row) {
+    const int y = static_cast<int>(row % Y), z = static_cast<int>(row / Y);
+    for (int w = threadIdx.x; w < W; w += blockDim.x) {
+      const uint32_t* p = in + row * W + w;
+      const uint32_t c = __ldg(p);
+      const uint32_t l = w > 0 ? __ldg(p - 1) : 0u;
+      const uint32_t g = w + 1 < W ? __ldg(p + 1) : 0u;
+      uint32_t acc = c | __funnelshift_l(l, c, 1) | __funnelshift_r(c, g, 1);
+      if (y > 0) acc |= __ldg(p - W);
+      if (y + 1 < Y) acc |= __ldg(p + W);
+      if (z > 0) acc |= __ldg(p - plane_words);
+      if (z + 1 < Z) acc |= __ldg(p + plane_words);
+      if (w == W - 1) acc &= tail;
+      out[row * W + w] = acc;
+    }
+  }
+}
+
+// Legacy averaging (reference `_average_n_slices_torch`, biahub/deskew.py:71-96): mean over
+// groups of n slices of the DESKEWED stack, the last slice repeated to fill the last group.
+// fp32 sequential sum, true division (torch.mean over a short dimension).
+__global__ void __launch_bounds__(256)
+    average_slices_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t plane,
+                          int Z, int n, int64_t total) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t a = i / plane, r = i - a * plane;
+    float s = 0.0f;
+    for (int k = 0; k < n; ++k) {
+      const int64_t z = min(a * n + k, static_cast<int64_t>(Z - 1));
+      s = __fadd_rn(s, __ldcs(src + z * plane + r));
+    }
+    dst[i] = __fdiv_rn(s, static_cast<float>(n));
+  }
+}
+
+int average_slices_device(const float* src, int64_t z, int64_t plane, int n, float* dst,
+                          cudaStream_t stream) {
+  if (!src || !dst || z < 1 || plane < 1 || n < 1 || z > 2147483647LL) {
+    set_error("average_slices: invalid argument");
+    return B2_ERR_INVALID;
+  }
+  const int64_t za = (z + n - 1) / n;
+  const int64_t total = za * plane;
+  int sms = 148;
+  sm_count(&sms);
+  const int64_t want = (total + 255) / 256;
+  const unsigned grid = static_cast<unsigned>(std::min<int64_t>(want, static_cast<int64_t>(sms) * 32));
+  average_slices_kernel<<<grid, 256, 0, stream>>>(src, dst, plane, static_cast<int>(z), n, total);
+  B2_CUDA(cudaGetLastError());
+  count_launch();
+  return B2_OK;
+}
+
 size_t fill_workspace_bytes(int64_t z, int64_t y, int64_t x) {
   const size_t words = static_cast<size_t>(z) * y * ((x + 31) / 32);
   const size_t arr = (words * 4 + 255) / 256 * 256;
   return 2 * arr + 256;
 }
 
+int fill_device_ex(float* vol, int64_t z, int64_t y, int64_t x, int use_mean, float fill_value,
+                   int iterations, int connectivity, void* ws, size_t ws_bytes, cudaStream_t stream);
+
 int fill_device(float* vol, int64_t z, int64_t y, int64_t x, int use_mean, float fill_value,
                 int iterations, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  return fill_device_ex(vol, z, y, x, use_mean, fill_value, iterations, 26, ws, ws_bytes, stream);
+}
+
+// connectivity 26: 3x3x3 cube per iteration (torch variant, max_pool3d); 6: 3-D cross per
+// iteration (numpy variant, scipy binary_dilation default)
+int fill_device_ex(float* vol, int64_t z, int64_t y, int64_t x, int use_mean, float fill_value,
+                   int iterations, int connectivity, void* ws, size_t ws_bytes, cudaStream_t stream) {
   if (!vol || !ws) {
     set_error("overhang_fill: null pointer");
     return B2_ERR_INVALID;
@@ -210,6 +286,10 @@ int fill_device(float* vol, int64_t z, int64_t y, int64_t x, int use_mean, float
   if (z < 1 || y < 1 || x < 1 || iterations < 0 || x > 2147483647LL || y > 2147483647LL ||
       z > 2147483647LL) {
     set_error("overhang_fill: invalid shape");
+    return B2_ERR_INVALID;
+  }
+  if (connectivity != 26 && connectivity != 6) {
+    set_error("overhang_fill: connectivity must be 26 (cube) or 6 (cross)");
     return B2_ERR_INVALID;
   }
   if (iterations > 15) {
@@ -236,12 +316,29 @@ int fill_device(float* vol, int64_t z, int64_t y, int64_t x, int use_mean, float
     return B2_ERR_INVALID;
   }
   const unsigned grid = static_cast<unsigned>((rows + kFillRowsPerCta - 1) / kFillRowsPerCta);
-  const int r = iterations;
+  int r = iterations;
   B2_CUDA(cudaMemsetAsync(scratch, 0, sizeof(FillScratch), stream));
   fill_bits_kernel<<<grid, kFillThreads, 0, stream>>>(vol, a, W, (int)x, rows);
   // one thread per word of the row: a block only as wide as the row has words
   const int bt = W >= kFillThreads ? kFillThreads : (W + 31) / 32 * 32;
-  fill_dilate_xy_kernel<<<grid, bt, 0, stream>>>(a, b, W, (int)y, r, rows);
+  if (connectivity == 6) {
+    // `iterations` cross dilations ping-pong between the two word arrays; the final pass below
+    // reads b, so an even count takes one more plain copy pass (xy dilation with r = 0)
+    uint32_t* cur = a;
+    uint32_t* nxt = b;
+    for (int it = 0; it < iterations; ++it) {
+      fill_dilate_cross_kernel<<<grid, bt, 0, stream>>>(cur, nxt, W, (int)x, (int)y, (int)z, rows);
+      count_launch();
+      std::swap(cur, nxt);
+    }
+    if (cur != b) {
+      fill_dilate_xy_kernel<<<grid, bt, 0, stream>>>(cur, b, W, (int)y, 0, rows);  // copy
+      count_launch();
+    }
+    r = 0;  // the final pass only reduces / fills
+  } else {
+    fill_dilate_xy_kernel<<<grid, bt, 0, stream>>>(a, b, W, (int)y, r, rows);
+  }
   if (use_mean) {
     fill_dilate_z_kernel<true><<<grid, kFillThreads, 0, stream>>>(vol, b, a, W, (int)x, (int)y, (int)z,
                                                                   r, 0.0f, scratch, rows);

@@ -18,6 +18,7 @@
 #include <condition_variable>
 #include <cstring>
 #include <functional>
+#include <memory>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -35,6 +36,17 @@ int affine_device(const void* src, int src_dtype, int64_t sz, int64_t sy, int64_
                   int order, int boundary, int scrub, int path, cudaStream_t stream,
                   int64_t src_row_pitch, int64_t dst_row_pitch);
 
+size_t fill_workspace_bytes(int64_t z, int64_t y, int64_t x);
+int fill_device(float* vol, int64_t z, int64_t y, int64_t x, int use_mean, float fill_value,
+                int iterations, void* ws, size_t ws_bytes, cudaStream_t stream);
+size_t spline_workspace_bytes(int64_t sz, int64_t sy, int64_t sx);
+int spline_prefilter_device(const void* src, int src_dtype, int64_t sz, int64_t sy, int64_t sx,
+                            int scrub, void* ws, size_t ws_bytes, const double** coef,
+                            cudaStream_t st);
+int spline_eval_device(const double* coef, int64_t sz, int64_t sy, int64_t sx, void* dst,
+                       int dst_dtype, int64_t oz, int64_t oy, int64_t ox, const double* M12,
+                       const int64_t* crop_start, cudaStream_t st);
+
 size_t flatfield_workspace_bytes(int64_t Y, int64_t X);
 int flatfield_begin(int64_t Y, int64_t X, void* ws, cudaStream_t stream);
 int flatfield_median(const void* src, int64_t Z, int64_t Y, int64_t X, void* ws, size_t ws_bytes,
@@ -46,6 +58,7 @@ namespace {
 
 constexpr size_t kSlabBytes = 48u << 20;  // target output bytes per slab
 constexpr int kRing = 3;                  // pinned staging ring depth (pageable callers)
+constexpr int kOutRing = 3;               // device output ring depth (slab i computes while i-1 travels)
 constexpr int kMaxDevices = 16;
 
 // ------------------------------------------------------------------ host thread pool
@@ -182,6 +195,21 @@ struct DeviceCtx {
 std::mutex g_mu;  // b2h_* calls are serialised per process (one worker process per GPU)
 DeviceCtx g_ctx[kMaxDevices];
 
+// Every b2h_* call selects its GPU with cudaSetDevice; the statically linked runtime shares the
+// primary context with the caller (torch), so the previous device is restored on every exit path.
+struct DeviceGuard {
+  int prev = -1;
+  DeviceGuard() {
+    if (cudaGetDevice(&prev) != cudaSuccess) {
+      (void)cudaGetLastError();
+      prev = -1;
+    }
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) (void)cudaSetDevice(prev);
+  }
+};
+
 bool is_pinned(const void* p) {
   cudaPointerAttributes a;
   if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
@@ -249,25 +277,45 @@ struct Band {
 
 struct Slab {
   std::vector<Band> bands;  // source data to upload before this slab's kernel
-  size_t out_off = 0, out_bytes = 0;
-  std::function<int(cudaStream_t)> launch;
+  size_t out_off = 0, out_bytes = 0;  // where the slab's result goes in the host output
+  // kernel(s) of this slab; `d_out` is the slab's slot of the device output ring (out_bytes long).
+  // Empty = nothing to launch (upload-only or download-only slab).
+  std::function<int(cudaStream_t, char* d_out)> launch;
+  const char* d_from = nullptr;  // download from here instead of the ring slot (resident results)
 };
 
-// Run the three-stream pipeline over `slabs`.
-int run_pipeline(DeviceCtx& c, const char* h_src, char* h_dst, std::vector<Slab>& slabs) {
+// Run the three-stream pipeline over `slabs`.  Device results live in a ring of kOutRing slots
+// (the largest slab each), not in a full-volume mirror: slab i's kernel waits for the download
+// of slab i - kOutRing.
+int run_pipeline_impl(DeviceCtx& c, const char* h_src, char* h_dst, std::vector<Slab>& slabs) {
   const bool src_pinned = is_pinned(h_src);
   const bool dst_pinned = is_pinned(h_dst);
   const size_t S = slabs.size();
+  size_t slot_bytes = 0;
+  for (const Slab& sl : slabs)
+    if (!sl.d_from) slot_bytes = std::max(slot_bytes, sl.out_bytes);
+  slot_bytes = (slot_bytes + 255) / 256 * 256;
+  if (slot_bytes) {
+    int grc = grow_device(&c.d_dst, &c.d_dst_bytes, slot_bytes * kOutRing);
+    if (grc) return grc;
+  }
   auto ev = [&](size_t kind, size_t i, cudaEvent_t* e) { return get_event(c, 3 * i + kind, e); };
   int rc;
 
-  auto unstage = [&](size_t j) -> int {
+  // pageable destination: results land in a pinned staging ring first; stage_owner[r] is the slab
+  // whose result currently sits in ring slot r (-1 = free)
+  long stage_owner[kRing];
+  for (int r = 0; r < kRing; ++r) stage_owner[r] = -1;
+  size_t n_staged = 0;
+  auto unstage = [&](int r) -> int {
+    if (stage_owner[r] < 0) return B2_OK;
+    const size_t j = static_cast<size_t>(stage_owner[r]);
     cudaEvent_t e;
     if ((rc = ev(2, j, &e))) return rc;
     B2_CUDA(cudaEventSynchronize(e));
     host_copy_2d(h_dst + slabs[j].out_off, slabs[j].out_bytes,
-                 static_cast<const char*>(c.h_out[j % kRing]), slabs[j].out_bytes,
-                 slabs[j].out_bytes, 1);
+                 static_cast<const char*>(c.h_out[r]), slabs[j].out_bytes, slabs[j].out_bytes, 1);
+    stage_owner[r] = -1;
     return B2_OK;
   };
 
@@ -310,40 +358,65 @@ int run_pipeline(DeviceCtx& c, const char* h_src, char* h_dst, std::vector<Slab>
     }
     B2_CUDA(cudaEventRecord(e_up, c.s_up));
 
-    // ---- kernel of this slab
+    // ---- kernel of this slab (its ring slot must have been downloaded)
     B2_CUDA(cudaStreamWaitEvent(c.s_run, e_up, 0));
-    if ((rc = sl.launch(c.s_run))) return rc;
+    char* d_slot = static_cast<char*>(c.d_dst) + (i % kOutRing) * slot_bytes;
+    if (i >= static_cast<size_t>(kOutRing)) {
+      cudaEvent_t prev_down;
+      if ((rc = ev(2, i - kOutRing, &prev_down))) return rc;
+      B2_CUDA(cudaStreamWaitEvent(c.s_run, prev_down, 0));
+    }
+    if (sl.launch && (rc = sl.launch(c.s_run, d_slot))) return rc;
     B2_CUDA(cudaEventRecord(e_run, c.s_run));
 
     // ---- download
     B2_CUDA(cudaStreamWaitEvent(c.s_down, e_run, 0));
-    const char* d_out = static_cast<const char*>(c.d_dst) + sl.out_off;
-    if (dst_pinned) {
+    const char* d_out = sl.d_from ? sl.d_from : d_slot;
+    if (!sl.out_bytes) {
+      // nothing to bring back (upload / compute only)
+    } else if (dst_pinned) {
       B2_CUDA(cudaMemcpyAsync(h_dst + sl.out_off, d_out, sl.out_bytes, cudaMemcpyDeviceToHost,
                               c.s_down));
     } else {
-      if (i >= static_cast<size_t>(kRing) && (rc = unstage(i - kRing))) return rc;
-      if ((rc = grow_pinned(&c.h_out[i % kRing], &c.h_out_bytes[i % kRing], sl.out_bytes)))
-        return rc;
-      B2_CUDA(cudaMemcpyAsync(c.h_out[i % kRing], d_out, sl.out_bytes, cudaMemcpyDeviceToHost,
-                              c.s_down));
+      const int r = static_cast<int>(n_staged++ % kRing);
+      if ((rc = unstage(r))) return rc;
+      if ((rc = grow_pinned(&c.h_out[r], &c.h_out_bytes[r], sl.out_bytes))) return rc;
+      B2_CUDA(cudaMemcpyAsync(c.h_out[r], d_out, sl.out_bytes, cudaMemcpyDeviceToHost, c.s_down));
+      stage_owner[r] = static_cast<long>(i);
     }
     B2_CUDA(cudaEventRecord(e_down, c.s_down));
   }
-  if (!dst_pinned) {
-    for (size_t j = (S > static_cast<size_t>(kRing) ? S - kRing : 0); j < S; ++j)
-      if ((rc = unstage(j))) return rc;
-  }
+  for (size_t k = 0; k < static_cast<size_t>(kRing); ++k)  // oldest first
+    if ((rc = unstage(static_cast<int>((n_staged + k) % kRing)))) return rc;
   B2_CUDA(cudaStreamSynchronize(c.s_down));
   B2_CUDA(cudaStreamSynchronize(c.s_up));
   return B2_OK;
 }
 
+int run_pipeline(DeviceCtx& c, const char* h_src, char* h_dst, std::vector<Slab>& slabs) {
+  const int rc = run_pipeline_impl(c, h_src, h_dst, slabs);
+  if (rc) {
+    // a failed step must not leave copies in flight that target the caller's arrays (or pooled
+    // pinned blocks): drain all three streams, keeping the first error for the caller
+    (void)cudaStreamSynchronize(c.s_up);
+    (void)cudaStreamSynchronize(c.s_run);
+    (void)cudaStreamSynchronize(c.s_down);
+    (void)cudaGetLastError();
+  }
+  return rc;
+}
+
 }  // namespace
 
-int host_deskew(const void* h_src, int src_dtype, int64_t Zi, int64_t Yi, int64_t Xi, float* h_dst,
-                int64_t Zavg, int64_t Yo, int64_t Xo, int64_t Zo_full, int N, float px32,
-                float pxct32, float off32, int device) {
+// fill_mode: 0 = none, 1 = overhang fill with the mean of the un-masked voxels, 2 = with
+// fill_value (reference biahub/deskew.py:538-540 -> _fill_overhang_torch).  The fill needs the
+// whole deskewed volume (global mask dilation + mean), so in that mode the deskew slabs stay on
+// the device, the fill runs once after the last slab, and the download slabs follow; uploads,
+// deskew kernels and (afterwards) the downloads still overlap.
+int host_deskew_fill(const void* h_src, int src_dtype, int64_t Zi, int64_t Yi, int64_t Xi,
+                     float* h_dst, int64_t Zavg, int64_t Yo, int64_t Xo, int64_t Zo_full, int N,
+                     float px32, float pxct32, float off32, int fill_mode, float fill_value,
+                     int device) {
   if (!h_src || !h_dst) {
     set_error("b2h_deskew: null pointer");
     return B2_ERR_INVALID;
@@ -357,7 +430,12 @@ int host_deskew(const void* h_src, int src_dtype, int64_t Zi, int64_t Yi, int64_
     set_error("b2h_deskew: invalid shape");
     return B2_ERR_INVALID;
   }
+  if (fill_mode < 0 || fill_mode > 2) {
+    set_error("b2h_deskew_fill: fill_mode must be 0, 1 (mean) or 2 (constant)");
+    return B2_ERR_INVALID;
+  }
   std::lock_guard<std::mutex> lock(g_mu);
+  DeviceGuard guard;
   DeviceCtx* c = nullptr;
   int rc = get_ctx(device, &c);
   if (rc) return rc;
@@ -365,7 +443,15 @@ int host_deskew(const void* h_src, int src_dtype, int64_t Zi, int64_t Yi, int64_
   const size_t in_bytes = static_cast<size_t>(Zi) * Yi * Xi * es;
   const size_t out_bytes = static_cast<size_t>(Zavg) * Yo * Xo * sizeof(float);
   if ((rc = grow_device(&c->d_src, &c->d_src_bytes, in_bytes))) return rc;
-  if ((rc = grow_device(&c->d_dst, &c->d_dst_bytes, out_bytes))) return rc;
+  float* d_full = nullptr;  // fill mode: the whole deskewed volume stays resident
+  size_t fill_ws = 0;
+  if (fill_mode) {
+    fill_ws = fill_workspace_bytes(Zavg, Yo, Xo);
+    if ((rc = grow_device(&c->d_mid, &c->d_mid_bytes, out_bytes))) return rc;
+    if ((rc = grow_device(&c->d_ws, &c->d_ws_bytes, fill_ws))) return rc;
+    d_full = static_cast<float*>(c->d_mid);
+  }
+  void* d_ws = c->d_ws;
 
   // slabs of averaged slices [a0, a0+cnt): contiguous in dst; they read tilt rows
   // iy in [Yi - min((a0+cnt)*N, Yi), Yi - 1 - a0*N] of every scan plane
@@ -374,7 +460,6 @@ int host_deskew(const void* h_src, int src_dtype, int64_t Zi, int64_t Yi, int64_
   const size_t row_bytes = static_cast<size_t>(Xi) * es;
   std::vector<Slab> slabs;
   void* d_src = c->d_src;
-  float* d_dst = static_cast<float*>(c->d_dst);
   for (int64_t a0 = 0; a0 < Zavg; a0 += per_slab) {
     const int64_t cnt = std::min(per_slab, Zavg - a0);
     const int64_t iy_hi = Yi - 1 - a0 * N;
@@ -387,15 +472,36 @@ int host_deskew(const void* h_src, int src_dtype, int64_t Zi, int64_t Yi, int64_
     b.rows = static_cast<size_t>(Zi);
     s.bands.push_back(b);
     s.out_off = static_cast<size_t>(a0) * slice_bytes;
-    s.out_bytes = static_cast<size_t>(cnt) * slice_bytes;
-    s.launch = [=](cudaStream_t st) {
+    s.out_bytes = fill_mode ? 0 : static_cast<size_t>(cnt) * slice_bytes;
+    const bool last = a0 + cnt >= Zavg;
+    s.launch = [=](cudaStream_t st, char* d_out) {
       const int slab[4] = {0, static_cast<int>(Yi), static_cast<int>(a0), static_cast<int>(cnt)};
-      return deskew_device(d_src, src_dtype, Zi, Yi, Xi, d_dst + a0 * Yo * Xo, Zavg, Yo, Xo,
-                           Zo_full, N, px32, pxct32, off32, B2_PATH_AUTO, st, slab, 0);
+      float* dst = fill_mode ? d_full + a0 * Yo * Xo : reinterpret_cast<float*>(d_out);
+      int r = deskew_device(d_src, src_dtype, Zi, Yi, Xi, dst, Zavg, Yo, Xo, Zo_full, N, px32,
+                            pxct32, off32, B2_PATH_AUTO, st, slab, 0);
+      if (r || !fill_mode || !last) return r;
+      return fill_device(d_full, Zavg, Yo, Xo, fill_mode == 1, fill_value, 3, d_ws, fill_ws, st);
     };
     slabs.push_back(std::move(s));
   }
+  if (fill_mode) {  // download slabs of the filled, resident volume
+    for (int64_t a0 = 0; a0 < Zavg; a0 += per_slab) {
+      const int64_t cnt = std::min(per_slab, Zavg - a0);
+      Slab s;
+      s.out_off = static_cast<size_t>(a0) * slice_bytes;
+      s.out_bytes = static_cast<size_t>(cnt) * slice_bytes;
+      s.d_from = reinterpret_cast<const char*>(d_full) + s.out_off;
+      slabs.push_back(std::move(s));
+    }
+  }
   return run_pipeline(*c, static_cast<const char*>(h_src), reinterpret_cast<char*>(h_dst), slabs);
+}
+
+int host_deskew(const void* h_src, int src_dtype, int64_t Zi, int64_t Yi, int64_t Xi, float* h_dst,
+                int64_t Zavg, int64_t Yo, int64_t Xo, int64_t Zo_full, int N, float px32,
+                float pxct32, float off32, int device) {
+  return host_deskew_fill(h_src, src_dtype, Zi, Yi, Xi, h_dst, Zavg, Yo, Xo, Zo_full, N, px32,
+                          pxct32, off32, 0, 0.0f, device);
 }
 
 int host_affine(const void* h_src, int src_dtype, int64_t sz, int64_t sy, int64_t sx, float* h_dst,
@@ -415,15 +521,14 @@ int host_affine(const void* h_src, int src_dtype, int64_t sz, int64_t sy, int64_
   }
   if (oz == 0 || oy == 0 || ox == 0) return B2_OK;
   std::lock_guard<std::mutex> lock(g_mu);
+  DeviceGuard guard;
   DeviceCtx* c = nullptr;
   int rc = get_ctx(device, &c);
   if (rc) return rc;
   const size_t es = elem_size(src_dtype);
   const size_t plane_in = static_cast<size_t>(sy) * sx * es;
   const size_t in_bytes = static_cast<size_t>(sz) * plane_in;
-  const size_t out_bytes = static_cast<size_t>(oz) * oy * ox * sizeof(float);
   if ((rc = grow_device(&c->d_src, &c->d_src_bytes, in_bytes))) return rc;
-  if ((rc = grow_device(&c->d_dst, &c->d_dst_bytes, out_bytes))) return rc;
 
   const int64_t c0[3] = {crop_start ? crop_start[0] : 0, crop_start ? crop_start[1] : 0,
                          crop_start ? crop_start[2] : 0};
@@ -431,7 +536,6 @@ int host_affine(const void* h_src, int src_dtype, int64_t sz, int64_t sy, int64_
   const int64_t per_slab = std::max<int64_t>(1, static_cast<int64_t>(kSlabBytes / plane_out));
   std::vector<Slab> slabs;
   void* d_src = c->d_src;
-  float* d_dst = static_cast<float*>(c->d_dst);
   std::vector<double> M(M12, M12 + 12);
   int64_t up_lo = 0, up_hi = 0;  // source planes [up_lo, up_hi) already scheduled for upload
   bool any = false;
@@ -479,10 +583,10 @@ int host_affine(const void* h_src, int src_dtype, int64_t sz, int64_t sy, int64_
     }
     s.out_off = static_cast<size_t>(z0) * plane_out;
     s.out_bytes = static_cast<size_t>(cnt) * plane_out;
-    s.launch = [=](cudaStream_t st) {
+    s.launch = [=](cudaStream_t st, char* d_out) {
       const int64_t crop[3] = {c0[0] + z0, c0[1], c0[2]};
-      return affine_device(d_src, src_dtype, sz, sy, sx, d_dst + z0 * oy * ox, cnt, oy, ox,
-                           M.data(), crop, order, boundary, scrub, B2_PATH_AUTO, st, 0, 0);
+      return affine_device(d_src, src_dtype, sz, sy, sx, reinterpret_cast<float*>(d_out), cnt, oy,
+                           ox, M.data(), crop, order, boundary, scrub, B2_PATH_AUTO, st, 0, 0);
     };
     slabs.push_back(std::move(s));
   }
@@ -514,6 +618,7 @@ int host_deskew_affine(const void* h_src, int src_dtype, int64_t Zi, int64_t Yi,
   }
   if (oz == 0 || oy == 0 || ox == 0) return B2_OK;
   std::lock_guard<std::mutex> lock(g_mu);
+  DeviceGuard guard;
   DeviceCtx* c = nullptr;
   int rc = get_ctx(device, &c);
   if (rc) return rc;
@@ -524,10 +629,8 @@ int host_deskew_affine(const void* h_src, int src_dtype, int64_t Zi, int64_t Yi,
   const size_t plane_out = static_cast<size_t>(oy) * ox * sizeof(float);
   if ((rc = grow_device(&c->d_src, &c->d_src_bytes, in_bytes))) return rc;
   if ((rc = grow_device(&c->d_mid, &c->d_mid_bytes, mid_bytes))) return rc;
-  if ((rc = grow_device(&c->d_dst, &c->d_dst_bytes, static_cast<size_t>(oz) * plane_out))) return rc;
   void* d_src = c->d_src;
   float* d_mid = static_cast<float*>(c->d_mid);
-  float* d_dst = static_cast<float*>(c->d_dst);
 
   // need[z]: the last deskewed plane output plane z reads (+2: upper tap and a clamped neighbour)
   const int64_t c0[3] = {crop_start ? crop_start[0] : 0, crop_start ? crop_start[1] : 0,
@@ -572,14 +675,14 @@ int host_deskew_affine(const void* h_src, int src_dtype, int64_t Zi, int64_t Yi,
     zdone = znext;
     s.out_off = static_cast<size_t>(z0) * plane_out;
     s.out_bytes = static_cast<size_t>(zc) * plane_out;
-    s.launch = [=](cudaStream_t st) {
+    s.launch = [=](cudaStream_t st, char* d_out) {
       const int slab[4] = {0, static_cast<int>(Yi), static_cast<int>(a0), static_cast<int>(cnt)};
       int r = deskew_device(d_src, src_dtype, Zi, Yi, Xi, d_mid + a0 * Yo * pitch, Zavg, Yo, Xo,
                             Zo_full, N, px32, pxct32, off32, B2_PATH_AUTO, st, slab, pitch);
       if (r || zc == 0) return r;
       const int64_t crop[3] = {c0[0] + z0, c0[1], c0[2]};
-      return affine_device(d_mid, B2_DTYPE_F32, Zavg, Yo, Xo, d_dst + z0 * oy * ox, zc, oy, ox,
-                           M.data(), crop, order, boundary, scrub, B2_PATH_AUTO, st, pitch, 0);
+      return affine_device(d_mid, B2_DTYPE_F32, Zavg, Yo, Xo, reinterpret_cast<float*>(d_out), zc,
+                           oy, ox, M.data(), crop, order, boundary, scrub, B2_PATH_AUTO, st, pitch, 0);
     };
     slabs.push_back(std::move(s));
   }
@@ -606,6 +709,7 @@ int host_flatfield(const void* h_src, int64_t Z, int64_t Y, int64_t X, void* h_d
     return B2_ERR_INVALID;
   }
   std::lock_guard<std::mutex> lock(g_mu);
+  DeviceGuard guard;
   DeviceCtx* c = nullptr;
   int rc = get_ctx(device, &c);
   if (rc) return rc;
@@ -614,10 +718,12 @@ int host_flatfield(const void* h_src, int64_t Z, int64_t Y, int64_t X, void* h_d
   const size_t plane_out = static_cast<size_t>(Y) * X * osz;
   const size_t ws_bytes = flatfield_workspace_bytes(Y, X);
   if ((rc = grow_device(&c->d_src, &c->d_src_bytes, static_cast<size_t>(Z) * plane_in))) return rc;
-  if ((rc = grow_device(&c->d_dst, &c->d_dst_bytes, static_cast<size_t>(Z) * plane_out))) return rc;
   if ((rc = grow_device(&c->d_ws, &c->d_ws_bytes, ws_bytes))) return rc;
+  // the apply kernel indexes the whole result volume: it stays resident (d_mid) and the slabs
+  // are downloaded from there
+  if ((rc = grow_device(&c->d_mid, &c->d_mid_bytes, static_cast<size_t>(Z) * plane_out))) return rc;
   void* d_src = c->d_src;
-  void* d_dst = c->d_dst;
+  void* d_dst = c->d_mid;
   void* d_ws = c->d_ws;
 
   std::vector<Slab> slabs;
@@ -634,7 +740,7 @@ int host_flatfield(const void* h_src, int64_t Z, int64_t Y, int64_t X, void* h_d
     b.rows = static_cast<size_t>(Z);
     s.bands.push_back(b);
     const bool first = y0 == 0;
-    s.launch = [=](cudaStream_t st) {
+    s.launch = [=](cudaStream_t st, char*) {
       int r = first ? flatfield_begin(Y, X, d_ws, st) : B2_OK;
       if (r) return r;
       return flatfield_median(d_src, Z, Y, X, d_ws, ws_bytes, y0 * X, cnt * X, st);
@@ -647,8 +753,85 @@ int host_flatfield(const void* h_src, int64_t Z, int64_t Y, int64_t X, void* h_d
     Slab s;
     s.out_off = static_cast<size_t>(z0) * plane_out;
     s.out_bytes = static_cast<size_t>(cnt) * plane_out;
-    s.launch = [=](cudaStream_t st) {
+    s.d_from = static_cast<const char*>(d_dst) + s.out_off;
+    s.launch = [=](cudaStream_t st, char*) {
       return flatfield_apply(d_src, Z, Y, X, d_dst, dst_dtype, d_ws, ws_bytes, z0, cnt, st);
+    };
+    slabs.push_back(std::move(s));
+  }
+  return run_pipeline(*c, static_cast<const char*>(h_src), static_cast<char*>(h_dst), slabs);
+}
+
+// Cubic-spline warp (reference method="scipy") with host buffers: source planes are uploaded in
+// ~48 MB pieces, the last piece triggers the three prefilter passes (they need the whole volume),
+// then slabs of output planes are evaluated and downloaded, slab i+1 computing while slab i travels.
+int host_affine_spline(const void* h_src, int src_dtype, int64_t sz, int64_t sy, int64_t sx,
+                       void* h_dst, int dst_dtype, int64_t oz, int64_t oy, int64_t ox,
+                       const double* M12, const int64_t* crop_start, int scrub, int device) {
+  if (!h_src || !h_dst || !M12) {
+    set_error("b2h_affine3d_spline3: null pointer");
+    return B2_ERR_INVALID;
+  }
+  if (src_dtype != B2_DTYPE_U16 && src_dtype != B2_DTYPE_F32) {
+    set_error("b2h_affine3d_spline3: unknown src_dtype %d", src_dtype);
+    return B2_ERR_INVALID;
+  }
+  if (dst_dtype != B2_DTYPE_U16 && dst_dtype != B2_DTYPE_F32) {
+    set_error("b2h_affine3d_spline3: dst_dtype must be uint16 or float32");
+    return B2_ERR_INVALID;
+  }
+  if (sz < 1 || sy < 1 || sx < 1 || oz < 0 || oy < 0 || ox < 0) {
+    set_error("b2h_affine3d_spline3: invalid shape");
+    return B2_ERR_INVALID;
+  }
+  if (oz == 0 || oy == 0 || ox == 0) return B2_OK;
+  std::lock_guard<std::mutex> lock(g_mu);
+  DeviceGuard guard;
+  DeviceCtx* c = nullptr;
+  int rc = get_ctx(device, &c);
+  if (rc) return rc;
+  const size_t es = elem_size(src_dtype);
+  const size_t plane_in = static_cast<size_t>(sy) * sx * es;
+  const size_t ws_bytes = spline_workspace_bytes(sz, sy, sx);
+  if ((rc = grow_device(&c->d_src, &c->d_src_bytes, static_cast<size_t>(sz) * plane_in))) return rc;
+  if ((rc = grow_device(&c->d_mid, &c->d_mid_bytes, ws_bytes))) return rc;
+  void* d_src = c->d_src;
+  void* d_ws = c->d_mid;
+  const int64_t c0[3] = {crop_start ? crop_start[0] : 0, crop_start ? crop_start[1] : 0,
+                         crop_start ? crop_start[2] : 0};
+  std::vector<double> M(M12, M12 + 12);
+  // the prefilter publishes the coefficient pointer for the evaluation slabs that follow it in
+  // stream order (host-side hand-over inside this call)
+  auto coef = std::make_shared<const double*>(nullptr);
+
+  std::vector<Slab> slabs;
+  const int64_t up = std::max<int64_t>(1, static_cast<int64_t>(kSlabBytes / plane_in));
+  for (int64_t p0 = 0; p0 < sz; p0 += up) {
+    const int64_t cnt = std::min(up, sz - p0);
+    Slab s;
+    Band b;
+    b.off = static_cast<size_t>(p0) * plane_in;
+    b.pitch = b.width = static_cast<size_t>(cnt) * plane_in;
+    b.rows = 1;
+    s.bands.push_back(b);
+    if (p0 + cnt >= sz)
+      s.launch = [=](cudaStream_t st, char*) {
+        return spline_prefilter_device(d_src, src_dtype, sz, sy, sx, scrub, d_ws, ws_bytes,
+                                       coef.get(), st);
+      };
+    slabs.push_back(std::move(s));
+  }
+  const size_t osz = dst_dtype == B2_DTYPE_U16 ? 2 : 4;
+  const size_t plane_out = static_cast<size_t>(oy) * ox * osz;
+  const int64_t per_slab = std::max<int64_t>(1, static_cast<int64_t>(kSlabBytes / plane_out));
+  for (int64_t z0 = 0; z0 < oz; z0 += per_slab) {
+    const int64_t cnt = std::min(per_slab, oz - z0);
+    Slab s;
+    s.out_off = static_cast<size_t>(z0) * plane_out;
+    s.out_bytes = static_cast<size_t>(cnt) * plane_out;
+    s.launch = [=](cudaStream_t st, char* d_out) {
+      const int64_t crop[3] = {c0[0] + z0, c0[1], c0[2]};
+      return spline_eval_device(*coef, sz, sy, sx, d_out, dst_dtype, cnt, oy, ox, M.data(), crop, st);
     };
     slabs.push_back(std::move(s));
   }
@@ -657,6 +840,7 @@ int host_flatfield(const void* h_src, int64_t Z, int64_t Y, int64_t X, void* h_d
 
 int host_release() {
   std::lock_guard<std::mutex> lock(g_mu);
+  DeviceGuard guard;
   for (int d = 0; d < kMaxDevices; ++d) {
     DeviceCtx& c = g_ctx[d];
     if (!c.init) continue;

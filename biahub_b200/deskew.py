@@ -24,8 +24,9 @@ from ._device import (check_out, device_source, host_source, is_torch_tensor, pa
                       resolve_device, row_pitch)
 
 __all__ = [
-    "_average_n_slices", "_get_averaged_shape", "_get_transform_matrix", "get_deskewed_data_shape",
-    "fast_deskew_zyx", "deskew_zyx", "_fast_deskew_czyx", "_deskew_czyx", "deskew_scalars",
+    "_average_n_slices", "_average_n_slices_torch", "_get_averaged_shape", "_get_transform_matrix",
+    "get_deskewed_data_shape", "fast_deskew_zyx", "deskew_zyx", "_fast_deskew_czyx", "_deskew_czyx",
+    "deskew_scalars",
 ]
 
 
@@ -115,6 +116,33 @@ def _average_n_slices(data, average_window_width=1):
     return data.reshape((data.shape[0] // w, w) + data.shape[1:]).mean(axis=1)
 
 
+def _average_n_slices_torch(data, average_window_width: int):
+    """Average a CUDA float32 tensor over groups of slices along axis 0, the last slice repeated
+    to fill the last group (reference deskew.py:71-96).  Runs ``b2_average_slices``; the
+    production path fuses the averaging into the deskew kernel and never calls this — the legacy
+    ``deskew_zyx`` does (reference deskew.py:438-440)."""
+    import torch
+
+    w = int(average_window_width)
+    if w == 1:
+        return data
+    if w < 1:
+        raise ValueError("average_window_width must be >= 1")
+    if not (is_torch_tensor(data) and data.is_cuda):
+        raise RuntimeError("_average_n_slices_torch computes on the GPU only: pass a CUDA tensor "
+                           "(no CPU fallback)")
+    src = data.to(torch.float32).contiguous()
+    Z = int(src.shape[0])
+    plane = int(np.prod(src.shape[1:])) if src.ndim > 1 else 1
+    out = torch.empty((-(-Z // w),) + tuple(src.shape[1:]), dtype=torch.float32, device=src.device)
+    if out.numel():
+        with torch.cuda.device(src.device):
+            _cabi.check(_cabi.lib().b2_average_slices(
+                src.data_ptr(), Z, plane, w, out.data_ptr(),
+                torch.cuda.current_stream().cuda_stream))
+    return out
+
+
 # ------------------------------------------------------------------------------------------
 # device path
 # ------------------------------------------------------------------------------------------
@@ -179,32 +207,21 @@ def fast_deskew_zyx(
 
 def _deskew_host(zyx, device, ls_angle_deg, px_to_scan_ratio, keep_overhang, average_n_slices=1,
                  overhang_fill=0, out=None):
-    """numpy (Z, Y, X) → numpy float32 through the pinned-buffer host pipeline."""
-    do_fill, _, _ = _fill_args(keep_overhang, overhang_fill)
+    """numpy (Z, Y, X) → numpy float32 through the pinned-buffer host pipeline: slab uploads,
+    deskew kernels and downloads overlap (``b2h_deskew``); with ``keep_overhang`` and a non-zero
+    ``overhang_fill`` the deskewed slabs stay on the device, the fill runs once on the resident
+    volume and the slabs are downloaded afterwards (``b2h_deskew_fill``)."""
+    do_fill, use_mean, value = _fill_args(keep_overhang, overhang_fill)
     dev = resolve_device(device)
-    if do_fill:
-        # the fill needs the whole volume on the device between kernel and download
-        import torch
-
-        src, _ = host_source(zyx)
-        if src.dtype == np.uint16:
-            t = torch.from_numpy(src.view(np.int16)).to(f"cuda:{dev}").view(torch.uint16)
-        else:
-            t = torch.from_numpy(src).to(f"cuda:{dev}")
-        res = fast_deskew_zyx(t, ls_angle_deg, px_to_scan_ratio, keep_overhang, average_n_slices,
-                              overhang_fill)
-        out = check_out(out, tuple(res.shape))  # pooled pinned array when the caller gave none
-        torch.from_numpy(out).copy_(res)
-        return out
     src, code = host_source(zyx)
     if src.ndim != 3:
         raise ValueError("raw data must have ndim == 3 (Z, Y, X)")
     s = deskew_scalars(src.shape, ls_angle_deg, px_to_scan_ratio, keep_overhang, average_n_slices)
     out = check_out(out, (s["Zavg"], s["Yo"], s["Xo"]))
-    _cabi.check(_cabi.lib().b2h_deskew(
+    _cabi.check(_cabi.lib().b2h_deskew_fill(
         src.ctypes.data_as(ctypes.c_void_p), code, s["Zi"], s["Yi"], s["Xi"],
         out.ctypes.data_as(ctypes.c_void_p), s["Zavg"], s["Yo"], s["Xo"], s["Zo"], s["N"],
-        s["px32"], s["pxct32"], s["off32"], dev))
+        s["px32"], s["pxct32"], s["off32"], (1 if use_mean else 2) if do_fill else 0, value, dev))
     return out
 
 
@@ -218,10 +235,22 @@ def deskew_zyx(
     overhang_fill: Literal["zero", "mean"] = "zero",
     debug_plot_path: Path | None = None,
 ) -> np.ndarray:
-    """Legacy entry point (reference deskew.py:371-453, MONAI ``Affine`` path).  Routed to the
-    same fused kernel as the production path; ``device`` only selects the GPU (see _device.py).
-    Known differences from the MONAI arithmetic are listed in DESIGN.md (last averaged slice when
-    Y % N != 0; cube instead of cross dilation for ``overhang_fill="mean"``)."""
+    """Legacy entry point (reference deskew.py:371-453), with the legacy order of operations:
+
+    1. deskew every tilt row (``average_n_slices=1``) — the reference's MONAI ``Affine`` with
+       this matrix is a flip/transpose plus a 1-D lerp along the scan axis with zero padding, the
+       same sampling the production kernel does (MONAI's own fp32 rounding is unpinned: MONAI is
+       not installable here, DESIGN.md §2);
+    2. ``_average_n_slices_torch`` on the DESKEWED stack, the last deskewed slice repeated when
+       ``Y % N != 0`` (reference :438-440) — NOT the production path's padding of the input row;
+    3. ``overhang_fill="mean"`` with ``keep_overhang``: the numpy variant
+       ``_fill_overhang_with_mean`` (reference :277-336, 448-451): zero mask dilated three times
+       with scipy's default 3-D CROSS, filled with the mean of the un-masked voxels.
+
+    ``device`` only selects the GPU (see _device.py); ``debug_plot_path`` is accepted and
+    ignored (a matplotlib diagnostic of the reference)."""
+    import torch
+
     raw = np.asarray(raw_data)
     if raw.ndim != 3:
         raise ValueError("raw_data must have ndim == 3 (Z, Y, X)")
@@ -229,8 +258,29 @@ def deskew_zyx(
     get_deskewed_data_shape(raw.shape, ls_angle_deg, px_to_scan_ratio, keep_overhang)
     if overhang_fill not in ("zero", "mean"):
         raise ValueError("overhang_fill must be 'zero' or 'mean'")
-    return _deskew_host(raw, device, ls_angle_deg, px_to_scan_ratio, keep_overhang,
-                        average_n_slices, overhang_fill)
+    N = int(average_n_slices)
+    if N == 1 and not (keep_overhang and overhang_fill == "mean"):
+        return _deskew_host(raw, device, ls_angle_deg, px_to_scan_ratio, keep_overhang, 1, 0)
+    dev = resolve_device(device)
+    src, _ = host_source(raw)
+    with torch.cuda.device(dev):
+        if src.dtype == np.uint16:
+            t = torch.from_numpy(src.view(np.int16)).to(f"cuda:{dev}").view(torch.uint16)
+        else:
+            t = torch.from_numpy(src).to(f"cuda:{dev}")
+        res = _average_n_slices_torch(
+            fast_deskew_zyx(t, ls_angle_deg, px_to_scan_ratio, keep_overhang, 1, 0), N)
+        if keep_overhang and overhang_fill == "mean":
+            lib = _cabi.lib()
+            shape = tuple(int(v) for v in res.shape)
+            nbytes = lib.b2_overhang_fill_workspace(*shape)
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=res.device)
+            _cabi.check(lib.b2_overhang_fill_ex(
+                res.data_ptr(), *shape, 1, 0.0, 3, 6, ws.data_ptr(), nbytes,
+                torch.cuda.current_stream().cuda_stream))
+        out = check_out(None, tuple(res.shape))
+        torch.from_numpy(out).copy_(res)
+    return out
 
 
 # Adapt ZYX functions to CZYX — module-level for multiprocessing pickling (reference deskew.py:545-579)
@@ -240,11 +290,30 @@ def _deskew_czyx(data, **kwargs):
 
 def _fast_deskew_czyx(data, device="cuda", num_splits=1, out=None, **kwargs):
     """CZYX wrapper used by ``biahub deskew`` (reference deskew.py:551-579): takes ``data[0]``,
-    returns ``(1, Z', Y', X')`` float32.  ``num_splits`` is accepted for compatibility: the
-    kernel is tile-based and the host pipeline already streams the volume in slabs, so no
-    host-side split/concatenate is needed (splitting along input X is exact).
+    returns ``(1, Z', Y', X')`` float32.
+
+    ``num_splits`` caps device memory as in the reference (deskew.py:563-573): the input is split
+    along its X axis (``np.array_split``), every chunk is deskewed on its own — device buffers
+    are sized by the chunk — and lands in its rows of the output's Y axis (output Y = reversed
+    input X, rows are independent: bit-identical to the unsplit call unless an overhang fill is
+    requested, which then sees one chunk at a time exactly as in the reference).  With the
+    default ``num_splits=1`` the device holds one input volume plus a three-slab output ring.
     ``out`` (extension): optional float32 (Z', Y', X') destination, e.g. a pinned buffer."""
-    zyx = np.asarray(data)[0]
-    if int(num_splits) < 1:
+    zyx = np.asarray(data[0])   # index first: lazy (zarr/dask) inputs decode one channel only
+    num_splits = int(num_splits)
+    if num_splits < 1:
         raise ValueError("num_splits must be >= 1")
-    return _deskew_host(zyx, device, out=out, **kwargs)[None]
+    if num_splits == 1 or zyx.ndim != 3:
+        return _deskew_host(zyx, device, out=out, **kwargs)[None]
+    # (an overhang fill is applied per chunk, as the reference does: mask dilation and mean see
+    # only the chunk)
+    s = deskew_scalars(zyx.shape, kwargs["ls_angle_deg"], kwargs["px_to_scan_ratio"],
+                       kwargs["keep_overhang"], kwargs.get("average_n_slices", 1))
+    out = check_out(out, (s["Zavg"], s["Yo"], s["Xo"]))
+    bounds = np.cumsum([0] + [len(c) for c in np.array_split(np.arange(s["Xi"]), num_splits)])
+    for x0, x1 in zip(bounds[:-1], bounds[1:]):
+        if x1 == x0:
+            continue
+        part = _deskew_host(np.ascontiguousarray(zyx[:, :, x0:x1]), device, **kwargs)
+        out[:, s["Xi"] - x1:s["Xi"] - x0, :] = part   # output row y <- input column Xi-1-y
+    return out[None]

@@ -7,10 +7,14 @@ reference register.py:148-168, pinned by reference tests/test_affine.py:43-59) a
 float32 array; the resampling runs in libbiahub_b200.so instead of ANTs/ITK or scipy.
 
 ``method="ants"`` (default) uses the ITK boundary rule; ``interpolation`` accepts the two ANTs
-modes this path is specified for: ``"linear"`` (order 1) and ``"nearestneighbor"`` (order 0).
-``method="scipy"`` in the reference calls ``scipy.ndimage.affine_transform`` with its default
-cubic spline (order 3) — that is not a linear/nearest resampler and is not built here: it raises
-``NotImplementedError``.  ``affine_warp`` exposes order/boundary explicitly (scipy
+modes this path is specified for: ``"linear"`` (order 1) and ``"nearestneighbor"`` (order 0);
+ANTs' other interpolators (gaussian, bspline, windowed sinc, label modes) raise
+``NotImplementedError`` — there is no CPU fallback.
+``method="scipy"`` reproduces the reference's literal call
+``scipy.ndimage.affine_transform(zyx_data, matrix, output_shape_zyx)`` (register.py:272): cubic
+spline (order 3), ``mode="constant"``; ``output_shape_zyx`` lands in scipy's ``offset`` slot and
+is ignored for a homogeneous matrix, so the result has the INPUT's shape and dtype
+(``spline_warp``, csrc/b2_spline.cu).  ``affine_warp`` exposes order/boundary explicitly (scipy
 ``mode="constant"`` rule = the oracle's primary mode).
 """
 
@@ -27,7 +31,7 @@ from ._device import (check_out, device_source, host_source, is_torch_tensor, pa
 __all__ = [
     "get_3D_rescaling_matrix", "get_3D_rotation_matrix", "get_3D_fliplr_matrix",
     "convert_transform_to_ants", "convert_transform_to_numpy", "apply_affine_transform",
-    "affine_warp", "rescale_voxel_size", "ItkAffineParameters", "largest_interior_rectangle",
+    "affine_warp", "spline_warp", "rescale_voxel_size", "ItkAffineParameters", "largest_interior_rectangle",
     "find_lir", "find_overlapping_volume",
 ]
 
@@ -110,6 +114,12 @@ class ItkAffineParameters:
     def as_matrix(self) -> np.ndarray:
         return convert_transform_to_numpy(self)
 
+    def invert(self):
+        """``ants.ANTsTransform.invert()`` (reference biahub/estimate_registration.py:190, 330):
+        the inverse map as a new transform with a zero centre."""
+        inv = np.linalg.inv(self.as_matrix())
+        return ItkAffineParameters(np.concatenate([inv[:3, :3].ravel(), inv[:3, 3]]))
+
     def apply_to_image(self, image, reference=None, interpolation="linear"):
         """``ants.ANTsTransform.apply_to_image`` for the estimation loops that warp inside their
         optimisation (reference biahub/optimize_registration.py:111, registration/ants.py:204,
@@ -172,8 +182,10 @@ def _interpolation_order(interpolation) -> int:
     key = str(interpolation).lower()
     if key not in _INTERPOLATION_ORDER:
         raise NotImplementedError(
-            f"interpolation={interpolation!r}: the B200 path implements 'linear' and "
-            f"'nearestneighbor' (the modes BASELINE.json's north_star specifies)")
+            f"interpolation={interpolation!r}: the B200 path implements ANTs' 'linear' and "
+            f"'nearestneighbor' (the modes BASELINE.json's north_star specifies) and, through "
+            f"method='scipy', the cubic B-spline; ANTs' gaussian / bspline / windowed-sinc / "
+            f"label interpolators are not built and there is no CPU fallback")
     return _INTERPOLATION_ORDER[key]
 
 
@@ -239,6 +251,69 @@ def affine_warp(data, matrix, output_shape_zyx, order: int = 1, boundary: str = 
     return out
 
 
+def _scipy_round(values: np.ndarray, dtype) -> np.ndarray:
+    """scipy.ndimage's conversion of an interpolated value to an integer output dtype
+    (NI_GeometricTransform): unsigned ``t > 0 ? t + 0.5 : 0``, signed ``t ± 0.5``, clamped to the
+    dtype's range, truncated."""
+    info = np.iinfo(dtype)
+    t = values.astype(np.float64)
+    t = np.where(t > 0, t + 0.5, 0.0 if info.min == 0 else t - 0.5)
+    return np.trunc(np.clip(t, info.min, info.max)).astype(dtype)
+
+
+def spline_warp(data, matrix, crop_output_slicing=None, device=None, out=None):
+    """Cubic B-spline pull-warp of a (Z, Y, X) volume onto ITS OWN grid — the arithmetic of
+    reference ``method="scipy"`` (register.py:271-272: scipy order 3, ``mode="constant"``,
+    ``cval=0``, prefilter on; output dtype = input dtype).  numpy in → numpy out (host pipeline
+    ``b2h_affine3d_spline3``) or CUDA tensor in → CUDA tensor out (``b2_affine3d_spline3``).
+
+    uint16 → uint16 (scipy's round-half-up conversion in the kernel) and float32 → float32 run
+    natively; float64 is computed from its float32 cast and returned as float64; other integer
+    dtypes are computed in float32 and converted with scipy's rule on the host."""
+    lib = _cabi.lib()
+    m12 = _cabi.matrix12(matrix)
+    if is_torch_tensor(data):
+        import torch
+
+        if data.ndim != 3:
+            raise ValueError("expected a (Z, Y, X) tensor")
+        src, code = device_source(data)
+        starts, sizes = _crop_box(tuple(src.shape), crop_output_slicing)
+        with torch.cuda.device(src.device):
+            res = torch.empty(sizes, dtype=torch.uint16 if code == _cabi.DTYPE_U16 else torch.float32,
+                              device=src.device)
+            if res.numel():
+                nbytes = int(lib.b2_spline3_workspace(*src.shape))
+                ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=src.device)
+                ws_ptr = (ws.data_ptr() + 255) // 256 * 256
+                stream = torch.cuda.current_stream()
+                _cabi.check(lib.b2_affine3d_spline3(
+                    src.data_ptr(), code, *src.shape, res.data_ptr(), code, *sizes, m12,
+                    _cabi.int64x3(starts), 1, ws_ptr, nbytes, stream.cuda_stream))
+                ws.record_stream(stream)
+        return res
+    arr = np.asarray(data)
+    if arr.ndim != 3:
+        raise ValueError("expected a (Z, Y, X) array")
+    in_dtype = arr.dtype
+    if in_dtype == np.float64:
+        arr = np.nan_to_num(arr, nan=0)   # reference register.py:254, in the input dtype
+    src, code = host_source(arr)
+    starts, sizes = _crop_box(src.shape, crop_output_slicing)
+    native = in_dtype in (np.uint16, np.float32)
+    res = check_out(out if native else None, sizes, np.uint16 if code == _cabi.DTYPE_U16 else np.float32)
+    if res.size:
+        _cabi.check(lib.b2h_affine3d_spline3(
+            src.ctypes.data_as(ctypes.c_void_p), code, *src.shape,
+            res.ctypes.data_as(ctypes.c_void_p), code, *sizes, m12, _cabi.int64x3(starts), 1,
+            resolve_device(device)))
+    if native:
+        return res
+    if in_dtype.kind in "ui":
+        return _scipy_round(res, in_dtype)
+    return res.astype(in_dtype)
+
+
 def apply_affine_transform(
     zyx_data: np.ndarray,
     matrix: np.ndarray,
@@ -250,36 +325,42 @@ def apply_affine_transform(
     """Drop-in for reference ``apply_affine_transform`` (register.py:202-281).
 
     3-D (Z, Y, X) or 4-D (C, Z, Y, X) input; NaNs are scrubbed to 0 (and ±inf to ±float32 max,
-    ``np.nan_to_num`` semantics) on load; the result is float32 on ``output_shape_zyx`` cropped
-    to ``crop_output_slicing``.
+    ``np.nan_to_num`` semantics) on load.  ``method="ants"``: float32 result on
+    ``output_shape_zyx`` cropped to ``crop_output_slicing``.  ``method="scipy"``: cubic spline on
+    the INPUT's grid in the input's dtype, then cropped (see the module docstring); a 4-D input
+    is assigned channel by channel into a float32 ``(C,) + cropped output_shape`` array exactly
+    as the reference does, so a mismatch raises numpy's broadcast ``ValueError`` there too.
     """
     if method == "ants":
         order = _interpolation_order(interpolation)
         boundary = "itk"
-    elif method == "scipy":
-        raise NotImplementedError(
-            "method='scipy' means scipy.ndimage.affine_transform's default cubic spline "
-            "(order=3, reference register.py:272), which the B200 path does not implement; use "
-            "method='ants' or affine_warp(..., boundary='constant', order=0|1)")
-    else:
+    elif method != "scipy":
         raise ValueError(f"Unknown method {method}")
 
     ndim = zyx_data.ndim
     if ndim == 4:
-        _, sizes = _crop_box(output_shape_zyx, crop_output_slicing)
+        if method == "ants":
+            _, sizes = _crop_box(output_shape_zyx, crop_output_slicing)
+        elif crop_output_slicing is None:
+            sizes = tuple(int(v) for v in output_shape_zyx)
+        else:  # reference register.py:233-238: stop - start, unclipped
+            sizes = tuple(int(sl.stop - sl.start) for sl in crop_output_slicing)
         if is_torch_tensor(zyx_data):
             import torch
 
             return torch.stack([
-                affine_warp(zyx_data[c], matrix, output_shape_zyx, order, boundary,
-                            crop_output_slicing) for c in range(zyx_data.shape[0])])
+                apply_affine_transform(zyx_data[c], matrix, output_shape_zyx, method, interpolation,
+                                       crop_output_slicing).to(torch.float32)
+                for c in range(zyx_data.shape[0])])
         registered = np.zeros((zyx_data.shape[0],) + sizes, dtype=np.float32)
         for c in range(zyx_data.shape[0]):
-            registered[c] = affine_warp(zyx_data[c], matrix, output_shape_zyx, order, boundary,
-                                        crop_output_slicing)
+            registered[c] = apply_affine_transform(zyx_data[c], matrix, output_shape_zyx, method,
+                                                   interpolation, crop_output_slicing)
         return registered
     if ndim != 3:
         raise ValueError("zyx_data must be (Z, Y, X) or (C, Z, Y, X)")
+    if method == "scipy":
+        return spline_warp(zyx_data, matrix, crop_output_slicing)
     return affine_warp(zyx_data, matrix, output_shape_zyx, order, boundary, crop_output_slicing)
 
 

@@ -13,7 +13,7 @@
  *    NULL = legacy default stream), never synchronises, allocates nothing persistent.
  *  - b2h_* (host API): data pointers are HOST pointers; the library stages through its own pinned
  *    ring buffers, overlaps H2D / kernel / D2H on side streams and returns when `dst` is complete.
- *  - volumes are C-contiguous (Z, Y, X); output is always float32.
+ *  - volumes are C-contiguous (Z, Y, X); output is float32 unless an entry point says otherwise.
  *  - return value: 0 on success, otherwise a B2_ERR_* code (or a cudaError_t value + 1000);
  *    b2_last_error() returns a thread-local human-readable message for the last failure.
  *  - there is NO CPU fallback: without a usable sm_100 device every compute entry point fails.
@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define B2_ABI_VERSION 1
+#define B2_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define B2_API __attribute__((visibility("default")))
@@ -121,6 +121,21 @@ B2_API size_t b2_overhang_fill_workspace(int64_t z, int64_t y, int64_t x);
 B2_API int b2_overhang_fill(float* vol, int64_t z, int64_t y, int64_t x, int use_mean, float fill_value,
                      int iterations, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Same with the structuring element chosen: connectivity 26 = 3x3x3 cube per iteration (the torch
+ * variant above), 6 = 3-D cross per iteration = scipy.ndimage.binary_dilation's default, which the
+ * numpy variant `_fill_overhang_with_mean` of the legacy `deskew_zyx` uses
+ * (biahub/deskew.py:277-336, 448-451). */
+B2_API int b2_overhang_fill_ex(float* vol, int64_t z, int64_t y, int64_t x, int use_mean,
+                        float fill_value, int iterations, int connectivity, void* workspace,
+                        size_t workspace_bytes, void* stream);
+
+/* Legacy averaging of the DESKEWED stack (reference `_average_n_slices_torch`,
+ * biahub/deskew.py:71-96, called by `deskew_zyx` :438-440): dst[a] = mean of the n slices
+ * src[a*n .. a*n+n-1] of plane_elems floats each, the last slice repeated to fill the last
+ * group; dst holds ceil(z / n) slices. */
+B2_API int b2_average_slices(const float* src, int64_t z, int64_t plane_elems, int n, float* dst,
+                      void* stream);
+
 /*
  * Host-buffer pipeline (what the reference's per-(t,c) callables see: numpy in, numpy out —
  * biahub/deskew.py:551-579, biahub/register.py:202-281).  The volume is split into slabs;
@@ -135,6 +150,37 @@ B2_API int b2h_affine3d(const void* h_src, int src_dtype, int64_t sz, int64_t sy
                  float* h_dst, int64_t oz, int64_t oy, int64_t ox,
                  const double* M12, const int64_t* crop_start,
                  int order, int boundary, int scrub_nonfinite, int device);
+
+/* b2h_deskew followed by the overhang fill of the whole deskewed volume (reference
+ * biahub/deskew.py:538-540: `keep_overhang and overhang_fill != 0` -> _fill_overhang_torch
+ * :339-368).  fill_mode 0 = none (same as b2h_deskew), 1 = mean of the un-masked voxels,
+ * 2 = fill_value.  Uploads and deskew slabs overlap; the fill runs once on the resident volume;
+ * its slabs are then downloaded. */
+B2_API int b2h_deskew_fill(const void* h_src, int src_dtype, int64_t Zi, int64_t Yi, int64_t Xi,
+                    float* h_dst, int64_t Zavg, int64_t Yo, int64_t Xo, int64_t Zo_full,
+                    int average_n_slices, float px32, float pxct32, float off32, int fill_mode,
+                    float fill_value, int device);
+
+/*
+ * Cubic B-spline affine pull warp = reference `apply_affine_transform(method="scipy")`
+ * (biahub/register.py:271-272: scipy.ndimage.affine_transform with scipy's defaults order=3,
+ * mode="constant", cval=0, prefilter on).  float64 prefilter (mirror initialisation, as scipy)
+ * and float64 evaluation of the 4x4x4 mirror-extended taps; coordinates outside [0, n-1] -> 0.
+ *
+ *   src   (sz, sy, sx) uint16 or float32 (NaN/inf scrubbed on load when scrub_nonfinite)
+ *   dst   (oz, oy, ox) uint16 (scipy's integer conversion: round half up, clamped) or float32
+ *   workspace: b2_spline3_workspace(sz, sy, sx) bytes of device memory, 256-byte aligned
+ *   M12 / crop_start as in b2_affine3d.
+ */
+B2_API size_t b2_spline3_workspace(int64_t sz, int64_t sy, int64_t sx);
+B2_API int b2_affine3d_spline3(const void* src, int src_dtype, int64_t sz, int64_t sy, int64_t sx,
+                        void* dst, int dst_dtype, int64_t oz, int64_t oy, int64_t ox,
+                        const double* M12, const int64_t* crop_start, int scrub_nonfinite,
+                        void* workspace, size_t workspace_bytes, void* stream);
+B2_API int b2h_affine3d_spline3(const void* h_src, int src_dtype, int64_t sz, int64_t sy, int64_t sx,
+                         void* h_dst, int dst_dtype, int64_t oz, int64_t oy, int64_t ox,
+                         const double* M12, const int64_t* crop_start, int scrub_nonfinite,
+                         int device);
 
 /*
  * Chained unit of BASELINE configs[4]: deskew, then warp the deskewed float32 volume — the

@@ -258,3 +258,47 @@ def deskew_oracle_points(raw, ls_angle_deg, px_to_scan_ratio, keep_overhang, ave
         sk = _fma32(t1, w, (t0 * e).astype(_f32))
         acc = sk if acc is None else (acc + sk).astype(_f32)
     return (acc / _f32(N)).astype(_f32)
+
+
+# --------------------------------------------------------------------------------------
+# legacy `deskew_zyx` order of operations — reference biahub/deskew.py:371-453
+# --------------------------------------------------------------------------------------
+def average_n_slices_torch_oracle(vol, window):
+    """``_average_n_slices_torch`` (reference deskew.py:71-96): groups of ``window`` slices of the
+    DESKEWED stack, the last slice repeated to fill the last group; fp32 mean."""
+    vol = np.asarray(vol, dtype=_f32)
+    w = int(window)
+    if w == 1:
+        return vol
+    rem = vol.shape[0] % w
+    if rem:
+        vol = np.concatenate([vol, np.repeat(vol[-1:], w - rem, axis=0)], axis=0)
+    grouped = vol.reshape((vol.shape[0] // w, w) + vol.shape[1:])
+    acc = np.zeros(grouped.shape[:1] + grouped.shape[2:], dtype=_f32)
+    for k in range(w):   # sequential fp32 sum, then true division (torch.mean over a short dim)
+        acc = (acc + grouped[:, k]).astype(_f32)
+    return (acc / _f32(w)).astype(_f32)
+
+
+def fill_overhang_with_mean_oracle(vol, dilation_iterations=3):
+    """``_fill_overhang_with_mean`` (reference deskew.py:277-336, the numpy variant the legacy
+    path uses): zero mask, scipy ``binary_dilation`` with its default 3-D cross, fill with
+    ``vol[~mask].mean()``."""
+    from scipy.ndimage import binary_dilation
+
+    vol = np.asarray(vol, dtype=_f32)
+    mask = binary_dilation(vol == 0, iterations=dilation_iterations)
+    out = vol.copy()
+    out[mask] = vol[~mask].mean()
+    return out, mask
+
+
+def deskew_legacy_oracle(raw, ls_angle_deg, px_to_scan_ratio, keep_overhang, average_n_slices=1,
+                         overhang_fill="zero"):
+    """Legacy ``deskew_zyx``: deskew every tilt row, average the deskewed stack, numpy-variant
+    fill.  The deskew itself is the production sampling (MONAI's rounding is unpinned)."""
+    vol = deskew_oracle_numpy(raw, ls_angle_deg, px_to_scan_ratio, keep_overhang, 1)
+    vol = average_n_slices_torch_oracle(vol, average_n_slices)
+    if keep_overhang and overhang_fill == "mean":
+        vol, _ = fill_overhang_with_mean_oracle(vol)
+    return vol

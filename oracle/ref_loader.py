@@ -318,3 +318,88 @@ def load_reference_register_stabilize():
                 sys.modules[k] = v
     _REG = (reg, stab)
     return _REG
+
+
+# ------------------------------------------------------------------------------------------
+# estimation-loop modules: only their import-time name bindings matter
+# here (tests/test_patch.py checks that patch.install() re-points them), so every third-party
+# module they import and this container lacks (napari, dask, skimage, ...) becomes an inert stub.
+# ------------------------------------------------------------------------------------------
+class _StubModule(types.ModuleType):
+    def __getattr__(self, name):
+        if name.startswith("__"):
+            raise AttributeError(name)
+        return _Sink()
+
+
+# third-party packages the estimation modules import that this container lacks
+_ABSENT_THIRD_PARTY = ("napari", "dask", "skimage", "waveorder", "cmap", "imageio", "tifffile",
+                       "ultrack", "pystackreg", "stitch", "xarray", "zarr", "numcodecs",
+                       "sklearn_extra", "cellpose", "toolz", "numba", "llvmlite", "seaborn",
+                       "networkx", "ome_zarr", "tensorstore", "psutil_extra", "colorspacious")
+
+
+class _StubFinder:
+    """meta_path finder of last resort: the known-absent third-party packages above (and their
+    sub-modules) become inert stubs.  Never shadows ``biahub`` or anything installed."""
+
+    def __init__(self):
+        self.made = []
+
+    def find_spec(self, fullname, path=None, target=None):
+        import importlib.machinery
+
+        top = fullname.split(".")[0]
+        if top not in _ABSENT_THIRD_PARTY:
+            return None
+        self.made.append(fullname)
+        return importlib.machinery.ModuleSpec(fullname, self, is_package=True)
+
+    def create_module(self, spec):
+        mod = _StubModule(spec.name)
+        mod.__path__ = []
+        return mod
+
+    def exec_module(self, module):
+        pass
+
+
+def load_reference_estimation_modules():
+    """Import the reference modules whose warps the estimation loops run (biahub/
+    optimize_registration.py, registration/ants.py, registration/beads.py,
+    estimate_registration.py, core/transform.py) into ``sys.modules`` with the fake ants and
+    auto-stubbed third parties; returns {name: module}.  The reference package stays installed
+    as ``biahub`` in ``sys.modules`` until ``unload_reference_package()``."""
+    reg, stab = load_reference_register_stabilize()
+    sys.modules["ants"] = fake_ants_module()
+    sys.modules["largestinteriorrectangle"] = fake_lir_module()
+    pkg = types.ModuleType("biahub")
+    pkg.__path__ = [os.path.join(REFERENCE_ROOT, "biahub")]
+    sys.modules["biahub"] = pkg
+    sys.modules["biahub.register"] = reg
+    sys.modules["biahub.stabilize"] = stab
+    finder = _StubFinder()
+    sys.meta_path.append(finder)
+    out = {"biahub.register": reg, "biahub.stabilize": stab}
+    try:
+        for name in ("biahub.core.transform", "biahub.registration.utils",
+                     "biahub.optimize_registration", "biahub.registration.ants",
+                     "biahub.registration.beads", "biahub.estimate_registration"):
+            out[name] = importlib.import_module(name)
+    finally:
+        sys.meta_path.remove(finder)
+    return out
+
+
+def unload_reference_package():
+    """Drop the reference ``biahub`` package (and the fakes) from ``sys.modules``."""
+    global _LOADED, _REG
+    for name in [n for n in sys.modules if n == "biahub" or n.startswith("biahub.")]:
+        del sys.modules[name]
+    for name in ("ants", "largestinteriorrectangle"):
+        if getattr(sys.modules.get(name), "__fake__", False):
+            del sys.modules[name]
+    for name in [n for n, m in sys.modules.items() if isinstance(m, _StubModule)]:
+        del sys.modules[name]
+    _LOADED = None
+    _REG = None

@@ -153,9 +153,9 @@ def test_argument_validation_happens_before_gpu():
     with pytest.raises(ValueError, match="Unknown method"):
         b2.apply_affine_transform(np.ones((4, 4, 4)), np.eye(4), (4, 4, 4), method="cupy")
     with pytest.raises(NotImplementedError):
-        b2.apply_affine_transform(np.ones((4, 4, 4)), np.eye(4), (4, 4, 4), method="scipy")
-    with pytest.raises(NotImplementedError):
         b2.apply_affine_transform(np.ones((4, 4, 4)), np.eye(4), (4, 4, 4), interpolation="bspline")
+    with pytest.raises(ValueError):   # unit-step crop slices only
+        b2.spline_warp(np.ones((4, 4, 4), np.float32), np.eye(4), (slice(0, 4, 2),) * 3)
     with pytest.raises(ValueError):
         b2.affine_warp(np.ones((4, 4, 4)), np.eye(3), (4, 4, 4))
     with pytest.raises(ValueError, match="Dataset contains only overhang"):
