@@ -11,8 +11,15 @@ argument only selects WHICH GPU:
 * env ``BIAHUB_B200_DEVICE`` (``"K"`` or ``"cuda:K"``) overrides everything.
 
 Per-process default: ``LOCAL_RANK`` if set (torchrun / one process per GPU), else
-``SLURM_LOCALID``, else ``os.getpid() % device_count`` so that the spawn-ed pool workers of
-``process_single_position`` spread over the GPUs of a node.
+``SLURM_LOCALID``, else ``BIAHUB_B200_WORKER_INDEX``, else the index of this multiprocessing pool
+worker (``SpawnPoolWorker-k`` → k-1: the spawn-ed workers of ``process_single_position`` are
+numbered consecutively, so they spread evenly over the GPUs of a node where ``pid %`` could pile
+several onto one), else ``os.getpid()`` — always modulo the device count.
+
+Pinned host memory is a per-BOX budget: ``BIAHUB_B200_PINNED_POOL_MB`` (default 6144) is divided
+by ``BIAHUB_B200_WORKERS`` (the number of sibling worker processes on the box, default 1; set it
+to the ``num_workers`` the CLI runs with — the reference defaults to 16 per position,
+biahub/deskew.py:693-695) to give each process's result-pool cap.
 """
 
 from __future__ import annotations
@@ -32,14 +39,36 @@ def default_device() -> int:
         n = _cabi.device_count()
         if n <= 0:
             _cabi.require_device(0)  # raises with the library's message
-        for var in ("LOCAL_RANK", "SLURM_LOCALID"):
+        for var in ("LOCAL_RANK", "SLURM_LOCALID", "BIAHUB_B200_WORKER_INDEX"):
             v = os.environ.get(var)
             if v is not None and v.isdigit():
                 _default_device = int(v) % n
                 break
         else:
-            _default_device = os.getpid() % n
+            _default_device = worker_index() % n
     return _default_device
+
+
+def worker_index() -> int:
+    """Index of this process among its siblings: the multiprocessing pool-worker number when
+    there is one (``_identity`` of ``SpawnPoolWorker-k`` is ``(k,)``), else the pid."""
+    try:
+        import multiprocessing
+
+        ident = multiprocessing.current_process()._identity
+        if ident:
+            return int(ident[0]) - 1
+    except Exception:  # noqa: BLE001 - private attribute: fall back to the pid
+        pass
+    return os.getpid()
+
+
+def pinned_pool_cap_bytes() -> int:
+    """This process's share of the box-wide pinned result-pool budget."""
+    total_mb = int(os.environ.get("BIAHUB_B200_PINNED_POOL_MB", "6144"))
+    workers = os.environ.get("BIAHUB_B200_WORKERS", "1")
+    workers = int(workers) if workers.isdigit() and int(workers) > 0 else 1
+    return (total_mb << 20) // workers
 
 
 def resolve_device(device=None) -> int:
@@ -166,14 +195,15 @@ class PinnedResultPool:
     it to zarr and drop it.  A fresh pageable ``np.empty`` costs a staging copy out of the pinned
     ring plus the first-touch page faults of 1.5 GB per mantis volume — 2-3x the PCIe time.  Blocks
     from this pool are the DMA target themselves; a block is handed out again once the array (and
-    all its views) is gone.  Bounded by ``BIAHUB_B200_PINNED_POOL_MB`` (default 6144; 0 disables):
-    beyond that, results fall back to ordinary pageable arrays.
+    all its views) is gone.  Bounded by this process's share of ``BIAHUB_B200_PINNED_POOL_MB``
+    (box-wide, default 6144; 0 disables; divided by ``BIAHUB_B200_WORKERS``): beyond that, results
+    fall back to ordinary pageable arrays.
     """
 
     def __init__(self, alloc=None, cap_bytes=None):
         self._alloc = alloc or self._alloc_pinned
         if cap_bytes is None:
-            cap_bytes = int(os.environ.get("BIAHUB_B200_PINNED_POOL_MB", "6144")) << 20
+            cap_bytes = pinned_pool_cap_bytes()
         self.cap_bytes = cap_bytes
         self.free = []          # blocks: {"ptr": int, "nbytes": int, "keep": object}
         self.total_bytes = 0

@@ -221,6 +221,166 @@ __device__ __forceinline__ uint32_t brick_column_linear(const BrickCol& c, const
   return rest;
 }
 
+// ---- packed fp32 helpers: sm_100a executes two fp32 operations per FFMA2 / FADD2 / FMUL2
+// instruction on an aligned register pair (one issue slot instead of two); a scalar operand is
+// broadcast for free (ptxas folds `mov.b64 {w, w}` into the `.F32` operand form)
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 add2_rd(f32x2 a, f32x2 b) {  // round towards -inf
+  f32x2 r;
+  asm("add.rm.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+
+// the four in-plane taps at `a` (rows a / a + row_b, columns +0 / +1), loaded only when the cell
+// address differs from `a_prev`; otherwise the registers keep their value.  The compare lives inside
+// the asm block so that the predicate never round-trips through a register.
+template <typename T>
+__device__ __forceinline__ void brick_quad_moved(uint32_t a, uint32_t a_prev, uint32_t row_b, float& v00,
+                                                 float& v01, float& v10, float& v11);
+template <>
+__device__ __forceinline__ void brick_quad_moved<float>(uint32_t a, uint32_t a_prev, uint32_t row_b,
+                                                        float& v00, float& v01, float& v10, float& v11) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .u32 a1;\n"
+      "setp.ne.u32 p, %4, %5;\n"
+      "add.u32 a1, %4, %6;\n"
+      "@p ld.shared.f32 %0, [%4];\n"
+      "@p ld.shared.f32 %1, [%4+4];\n"
+      "@p ld.shared.f32 %2, [a1];\n"
+      "@p ld.shared.f32 %3, [a1+4];\n"
+      "}\n"
+      : "+f"(v00), "+f"(v01), "+f"(v10), "+f"(v11)
+      : "r"(a), "r"(a_prev), "r"(row_b));
+}
+template <>
+__device__ __forceinline__ void brick_quad_moved<uint16_t>(uint32_t a, uint32_t a_prev, uint32_t row_b,
+                                                           float& v00, float& v01, float& v10,
+                                                           float& v11) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .u32 a1;\n"
+      ".reg .b16 h0, h1, h2, h3;\n"
+      "setp.ne.u32 p, %4, %5;\n"
+      "add.u32 a1, %4, %6;\n"
+      "@p ld.shared.u16 h0, [%4];\n"
+      "@p ld.shared.u16 h1, [%4+2];\n"
+      "@p ld.shared.u16 h2, [a1];\n"
+      "@p ld.shared.u16 h3, [a1+2];\n"
+      "@p cvt.rn.f32.u16 %0, h0;\n"
+      "@p cvt.rn.f32.u16 %1, h1;\n"
+      "@p cvt.rn.f32.u16 %2, h2;\n"
+      "@p cvt.rn.f32.u16 %3, h3;\n"
+      "}\n"
+      : "+f"(v00), "+f"(v01), "+f"(v10), "+f"(v11)
+      : "r"(a), "r"(a_prev), "r"(row_b));
+}
+
+// One (y, x) column of a full-depth tile, order 1, FINITE taps (uint16, or float32 with the scrub:
+// a non-finite result sends the voxel to the exact path) — the packed-arithmetic form of
+// brick_column_linear.  The four in-plane taps of the two source planes sit in four register
+// PAIRS (lo half / hi half = the two planes); the upper plane of voxel k is the lower plane of
+// voxel k+1, so the halves swap roles from step to step (the loop is fully unrolled: the parity is
+// static) and only the upper plane is loaded — the lower one again only when the (y, x) cell moved.
+// Per voxel: 2 coordinate adds, 3 floors, 5 weight ops (y and x packed), 3 address, 1 compare,
+// 4 + 4 predicated LDS, 8 lerp instructions (3 FADD2 + 3 FFMA2 + 2 scalar), check + store.
+template <typename T, bool CHECK, bool LY>
+__device__ __forceinline__ uint32_t brick_column_packed(const BrickCol& c, const float (&mid)[3],
+                                                        const float (&half)[3],
+                                                        float* __restrict__ out) {
+  constexpr uint32_t es = static_cast<uint32_t>(sizeof(T));
+  const uint32_t abase = c.brick - 0x4B400000u * (c.plane_b + c.row_b + es);
+  uint32_t rest = 0;
+  float bad = 0.0f;  // turns NaN as soon as one voxel of the column is non-finite (v * 0 accumulates)
+  float qa[4] = {0.0f, 0.0f, 0.0f, 0.0f};  // lo halves: taps (y0,x0) (y0,x1) (y1,x0) (y1,x1) of one plane
+  float qb[4] = {0.0f, 0.0f, 0.0f, 0.0f};  // hi halves: the same taps of the other plane
+  uint32_t a_up = 0xffffffffu;
+  float uz = c.u0z;
+  f32x2 uyx = pk2(c.u0y, c.u0x);
+  const f32x2 myx = pk2(c.my, c.mx);
+  const f32x2 magic2 = pk2(kMagic, kMagic);
+  // the output pointer walks one plane per voxel as a BYTE pointer (one 64-bit add, no index scaling)
+  char* __restrict__ o = reinterpret_cast<char*>(out);
+  const int64_t plane_bytes = c.out_plane * 4;
+#pragma unroll
+  for (int k = 0; k < kBrTZ; ++k) {
+    bool interior = true;
+    if (CHECK) {
+      float uy, ux;
+      upk2(uyx, uy, ux);
+      interior = fabsf(uz - mid[0]) <= half[0] - kEdge && fabsf(uy - mid[1]) <= half[1] - kEdge &&
+                 fabsf(ux - mid[2]) <= half[2] - kEdge;
+    }
+    if (interior) {
+      const float tz = __fadd_rd(uz, kMagic);
+      const f32x2 tyx = add2_rd(uyx, magic2);
+      const float wz = uz - (tz - kMagic);
+      const f32x2 wyx = sub2(uyx, sub2(tyx, magic2));
+      float ty, tx, wy, wx;
+      upk2(tyx, ty, tx);
+      upk2(wyx, wy, wx);
+      const uint32_t a00 = static_cast<uint32_t>(__float_as_int(tz)) * c.plane_b +
+                           (static_cast<uint32_t>(__float_as_int(ty)) * c.row_b +
+                            (static_cast<uint32_t>(__float_as_int(tx)) * es + abase));
+      const uint32_t a10 = a00 + c.plane_b;
+      float (&lo)[4] = (k & 1) ? qb : qa;  // lower source plane of this voxel
+      float (&up)[4] = (k & 1) ? qa : qb;  // upper source plane: loaded now, lower plane next step
+      brick_quad_moved<T>(a00, a_up, c.row_b, lo[0], lo[1], lo[2], lo[3]);
+      up[0] = brick_elem<T>(a10);
+      up[1] = brick_elem<T>(a10 + es);
+      up[2] = brick_elem<T>(a10 + c.row_b);
+      up[3] = brick_elem<T>(a10 + c.row_b + es);
+      a_up = a10;
+      const f32x2 q00 = pk2(qa[0], qb[0]), q01 = pk2(qa[1], qb[1]);
+      const f32x2 q10 = pk2(qa[2], qb[2]), q11 = pk2(qa[3], qb[3]);
+      const f32x2 wx2 = pk2(wx, wx), wy2 = pk2(wy, wy);
+      const f32x2 x0 = fma2(wx2, sub2(q01, q00), q00);  // x lerp on row y0 of both planes
+      const f32x2 x1 = fma2(wx2, sub2(q11, q10), q10);  // ... on row y1
+      const f32x2 yy = fma2(wy2, sub2(x1, x0), x0);     // in-plane bilinear value of both planes
+      float pa, pb;
+      upk2(yy, pa, pb);
+      const float vlo = (k & 1) ? pb : pa, vup = (k & 1) ? pa : pb;
+      const float v = __fmaf_rn(wz, vup - vlo, vlo);
+      // a NaN/inf tap makes v non-finite; the voxel is stored anyway and the whole column is
+      // redone on the exact path (which applies the scrub per tap) after the loop
+      if (sizeof(T) == 4) bad = __fmaf_rn(v, 0.0f, bad);
+      brick_put<LY>(reinterpret_cast<float*>(o), v);
+    } else {
+      rest |= 1u << k;
+      a_up = 0xffffffffu;
+    }
+    uz += c.mz;
+    uyx = add2(uyx, myx);
+    o += plane_bytes;
+  }
+  return (bad != bad) ? 0xffu : rest;
+}
+
 template <typename T, int ORDER, int BOUNDARY, bool SCRUB, bool LY>
 __global__ void __launch_bounds__(kBrThreads, 4)
     affine_brick_kernel(const __grid_constant__ CUtensorMap src_map,
@@ -358,7 +518,10 @@ __global__ void __launch_bounds__(kBrThreads, 4)
       const BrickCol cc{brick, plane_b, row_b, out_plane, u0[0], u0[1], u0[2], mcol[0][0], mcol[1][0],
                         mcol[2][0]};
       uint32_t rest;
-      if (tile_in) {
+      if (SCRUB || sizeof(T) == 2) {  // finite taps: packed arithmetic
+        rest = tile_in ? brick_column_packed<T, false, LY>(cc, mid, half, out)
+                       : brick_column_packed<T, true, LY>(cc, mid, half, out);
+      } else if (tile_in) {
         rest = brick_column_linear<T, SCRUB, false, LY>(cc, mid, half, out);
       } else {
         rest = brick_column_linear<T, SCRUB, true, LY>(cc, mid, half, out);

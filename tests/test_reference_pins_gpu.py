@@ -50,7 +50,9 @@ def test_apply_affine_transform_matches_reference_goldens(golden_affine):
         else:
             finite = np.isfinite(want)
             assert np.array_equal(finite, np.isfinite(got)), n
-            assert np.abs(got[finite] - want[finite]).max() <= 1e-4 * max(_range(vol), 1.0), n
+            # taps scrubbed to +-FLT_MAX dominate their neighbourhood: relative term for those
+            tol = 1e-4 * _range(vol) + 1e-6 * np.abs(want[finite].astype(np.float64))
+            assert (np.abs(got[finite].astype(np.float64) - want[finite]) <= tol).all(), n
             if n in ("u8_identity", "ref_kat_translation"):
                 assert np.array_equal(got, want), n
 
@@ -68,7 +70,9 @@ def test_apply_stabilization_matches_reference_goldens(golden_affine):
         if n == "int_shift_3d":
             assert np.array_equal(got, want)
         else:
-            assert np.abs(got - want).max() <= 1e-4 * _range(np.nan_to_num(vol.astype(np.float64), posinf=0, neginf=0)), n
+            tol = (1e-4 * _range(np.nan_to_num(vol.astype(np.float64), posinf=0, neginf=0))
+                   + 1e-6 * np.abs(want.astype(np.float64)))
+            assert (np.abs(got.astype(np.float64) - want) <= tol).all(), n
 
 
 def test_find_overlapping_volume_matches_reference_goldens(golden_affine):
