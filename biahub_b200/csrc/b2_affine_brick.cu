@@ -221,39 +221,6 @@ __device__ __forceinline__ uint32_t brick_column_linear(const BrickCol& c, const
   return rest;
 }
 
-// ---- packed fp32 helpers: sm_100a executes two fp32 operations per FFMA2 / FADD2 / FMUL2
-// instruction on an aligned register pair (one issue slot instead of two); a scalar operand is
-// broadcast for free (ptxas folds `mov.b64 {w, w}` into the `.F32` operand form)
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
-  f32x2 r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
-  f32x2 r;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
-  f32x2 r;
-  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-__device__ __forceinline__ f32x2 add2_rd(f32x2 a, f32x2 b) {  // round towards -inf
-  f32x2 r;
-  asm("add.rm.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
-  f32x2 r;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-  return r;
-}
-
 // the four in-plane taps at `a` (rows a / a + row_b, columns +0 / +1), loaded only when the cell
 // address differs from `a_prev`; otherwise the registers keep their value.  The compare lives inside
 // the asm block so that the predicate never round-trips through a register.

@@ -138,6 +138,45 @@ __device__ __forceinline__ void st_global_cs4(float* p, float4 v) {
                : "memory");
 }
 
+// ---- packed fp32 helpers (round-to-nearest, no flush: IEEE-identical to the scalar ops): sm_100a executes two fp32 operations per FFMA2 / FADD2 / FMUL2
+// instruction on an aligned register pair (one issue slot instead of two); a scalar operand is
+// broadcast for free (ptxas folds `mov.b64 {w, w}` into the `.F32` operand form)
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 add2_rd(f32x2 a, f32x2 b) {  // round towards -inf
+  f32x2 r;
+  asm("add.rm.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 bc2(float v) { return pk2(v, v); }  // broadcast: a free .F32 operand
+
 template <typename T>
 __device__ __forceinline__ float to_f32(T v);
 template <>
