@@ -16,7 +16,14 @@
 
 namespace b2 {
 
-constexpr int kBrTZ = 8;
+// Tile depth along z.  A deep tile amortises the z halo of its source brick: the kernel is bound by
+// the L2 -> shared-memory traffic of the bricks (8-deep tiles: 13 source planes per 8 output planes
+// and 3.3 source voxels staged per output voxel — 6.5 GB per C3-sized volume at the ~5.5 TB/s the
+// TMA boxes reach, which IS the 1.18 ms of the r1 kernel; 16-deep tiles with tight margins: 2.2).
+// 16 when the brick then still allows 3 CTAs/SM, else 8; the unrolled column routine is
+// instantiated for both depths.
+constexpr int kBrTZ = 8;      // depth of the legacy column routine (non-finite float32 taps)
+constexpr int kBrTZMax = 16;
 // In-plane tile: 16 (y) x 32 (x) with lanes along x; LY variant 32 (y) x 16 (x) with lanes along y
 // for matrices that map output y onto source x (90-degree in-plane rotations: with lanes along x
 // a warp's taps walk a brick column, 8-way bank conflicts) — its output goes through a padded
@@ -27,11 +34,15 @@ constexpr int kBrThreads = 256;
 constexpr int kBrCols = (kBrLanes * kBrOther) / kBrThreads;  // (y, x) columns per thread
 constexpr int kBrRowStep = kBrThreads / kBrLanes;            // distance between a thread's columns
 constexpr int kBrOutPitch = kBrOther + 1;                    // LY: padded row pitch of the staged output
-constexpr int kBrStageBytes = kBrTZ * kBrLanes * kBrOutPitch * 4;
+constexpr int kBrStageBytes = kBrTZ * kBrLanes * kBrOutPitch * 4;  // LY tiles stay 8 deep
+// slack (voxels) added to both ends of a tile's back-projected hull before it is floored: covers
+// the rounding of the host's hull sums and the fp32 coordinate error of the fast path (~1e-5)
+constexpr double kBrGuard = 1.0e-4;
 constexpr float kEdge = 2.0e-3f;
 constexpr float kMagic = 12582912.0f;  // 1.5 * 2^23: (v + kMagic) - kMagic rounds v to nearest
 
 struct BrickGeom {
+  int TZ;          // tile depth along z (kBrTZMax or kBrTZ)
   int BZ, BY, BX;  // brick extent (elements)
   int bytes;       // BZ*BY*BX*sizeof(T)
   // hull of a full tile relative to its origin voxel: sum of the negative / positive parts of
@@ -105,15 +116,20 @@ __device__ __forceinline__ double coord_full(const double* m, double zf, double 
 // exact (float64) evaluation of one voxel with taps read from the brick
 template <typename T, int ORDER, int BOUNDARY, bool SCRUB>
 __device__ __noinline__ float brick_sample_exact(const AffineParams& p, uint32_t brick, int bz0,
-                                                 int by0, int bx0, int BY, int BX, int z, int y,
-                                                 int x) {
+                                                 int by0, int bx0, int BZ, int BY, int BX, int z,
+                                                 int y, int x) {
   const double zf = static_cast<double>(z + p.cz), yf = static_cast<double>(y + p.cy),
                xf = static_cast<double>(x + p.cx);
   const AxisTap tz = resolve_axis<ORDER, BOUNDARY>(coord_full(p.m, zf, yf, xf), p.sz);
   const AxisTap ty = resolve_axis<ORDER, BOUNDARY>(coord_full(p.m + 4, zf, yf, xf), p.sy);
   const AxisTap tx = resolve_axis<ORDER, BOUNDARY>(coord_full(p.m + 8, zf, yf, xf), p.sx);
   if (!(tz.inside && ty.inside && tx.inside)) return 0.0f;
+  // a tap with zero weight (the dropped neighbour of the ITK half-voxel band) may sit one element
+  // past the tight brick: clamp into it (the value is multiplied by 0, it only has to be loadable)
   auto tap = [&](int iz, int iy, int ix) {
+    iz = min(max(iz - bz0, 0), BZ - 1) + bz0;
+    iy = min(max(iy - by0, 0), BY - 1) + by0;
+    ix = min(max(ix - bx0, 0), BX - 1) + bx0;
     const uint32_t off = static_cast<uint32_t>(((iz - bz0) * BY + (iy - by0)) * BX + (ix - bx0));
     float v = brick_elem<T>(brick + off * static_cast<uint32_t>(sizeof(T)));
     if (SCRUB && sizeof(T) == 4) v = scrub_value(v);
@@ -276,10 +292,10 @@ __device__ __forceinline__ void brick_quad_moved<uint16_t>(uint32_t a, uint32_t 
 // static) and only the upper plane is loaded — the lower one again only when the (y, x) cell moved.
 // Per voxel: 2 coordinate adds, 3 floors, 5 weight ops (y and x packed), 3 address, 1 compare,
 // 4 + 4 predicated LDS, 8 lerp instructions (3 FADD2 + 3 FFMA2 + 2 scalar), check + store.
-template <typename T, bool CHECK, bool LY>
+template <typename T, bool CHECK, bool LY, int TZ>
 __device__ __forceinline__ uint32_t brick_column_packed(const BrickCol& c, const float (&mid)[3],
                                                         const float (&half)[3],
-                                                        float* __restrict__ out) {
+                                                        float* __restrict__ out, const int nz) {
   constexpr uint32_t es = static_cast<uint32_t>(sizeof(T));
   const uint32_t abase = c.brick - 0x4B400000u * (c.plane_b + c.row_b + es);
   uint32_t rest = 0;
@@ -294,8 +310,10 @@ __device__ __forceinline__ uint32_t brick_column_packed(const BrickCol& c, const
   // the output pointer walks one plane per voxel as a BYTE pointer (one 64-bit add, no index scaling)
   char* __restrict__ o = reinterpret_cast<char*>(out);
   const int64_t plane_bytes = c.out_plane * 4;
+  // partial-depth tiles (nz < TZ) compute every voxel of the column (the brick always covers a
+  // full tile) and only predicate the store
 #pragma unroll
-  for (int k = 0; k < kBrTZ; ++k) {
+  for (int k = 0; k < TZ; ++k) {
     bool interior = true;
     if (CHECK) {
       float uy, ux;
@@ -336,16 +354,16 @@ __device__ __forceinline__ uint32_t brick_column_packed(const BrickCol& c, const
       // a NaN/inf tap makes v non-finite; the voxel is stored anyway and the whole column is
       // redone on the exact path (which applies the scrub per tap) after the loop
       if (sizeof(T) == 4) bad = __fmaf_rn(v, 0.0f, bad);
-      brick_put<LY>(reinterpret_cast<float*>(o), v);
+      if (k < nz) brick_put<LY>(reinterpret_cast<float*>(o), v);
     } else {
-      rest |= 1u << k;
+      if (k < nz) rest |= 1u << k;
       a_up = 0xffffffffu;
     }
     uz += c.mz;
     uyx = add2(uyx, myx);
     o += plane_bytes;
   }
-  return (bad != bad) ? 0xffu : rest;
+  return (bad != bad) ? ((1u << nz) - 1u) : rest;
 }
 
 template <typename T, int ORDER, int BOUNDARY, bool SCRUB, bool LY>
@@ -366,11 +384,12 @@ __global__ void __launch_bounds__(kBrThreads, 4)
   const int tz_i = blockIdx.x % tiles_z;
   const int tx_i = (blockIdx.x / tiles_z) % tiles_x;
   const int ty_i = blockIdx.x / (tiles_z * tiles_x);
-  const int z0 = tz_i * kBrTZ, y0 = ty_i * kBrTY, x0 = tx_i * kBrTX;
-  const int nz = min(kBrTZ, p.oz - z0);
+  const int z0 = tz_i * g.TZ, y0 = ty_i * kBrTY, x0 = tx_i * kBrTX;
+  const int nz = min(g.TZ, p.oz - z0);
 
   // ---- brick origin: exact float64 coordinate of the tile origin + the host-computed hull of a
-  //      full tile (the 1e-6 guards absorb the rounding of the hull sums; the host guarantees
+  //      full tile (the kBrGuard slack absorbs the rounding of the hull sums and the fp32 error of
+  //      the fast path's coordinates; the host guarantees
   //      |coordinate| < 1e9 over the whole output so the int conversions are defined).
   //      CTA-uniform, so ONE thread evaluates it (float64, ~170 instructions), issues the TMA
   //      load and publishes the result through shared memory.
@@ -385,14 +404,14 @@ __global__ void __launch_bounds__(kBrThreads, 4)
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
       const double c = coord_full(p.m + 4 * d, zf, yf, xf);
-      tb0[d] = __double2int_rd(c + (g.neg[d] - 1e-6));
+      tb0[d] = __double2int_rd(c + (g.neg[d] - kBrGuard));
       // the hull of the tile misses the source (and its half-voxel ITK band) on this axis
-      outside = outside || tb0[d] >= n[d] + 1 || __double2int_rd(c + (g.pos[d] + 1e-6)) <= -2;
+      outside = outside || tb0[d] >= n[d] + 1 || __double2int_rd(c + (g.pos[d] + kBrGuard)) <= -2;
       // every tap of every voxel of a full tile is a valid source index, with >= 1 voxel margin
       inside = inside && tb0[d] >= 1;
       if (d == 2) tb0[d] &= ~(kVec - 1);  // innermost TMA coordinate must be 16-byte aligned
-      tbhi[d] = __double2int_rd(c + (g.pos[d] + 1e-6)) + 2;
-      inside = inside && tbhi[d] <= n[d] - 1;
+      tbhi[d] = __double2int_rd(c + (g.pos[d] + kBrGuard)) + 1;  // index of the last tap
+      inside = inside && tbhi[d] <= n[d] - 2;
       s_geo[d] = tb0[d];
       s_geo[3 + d] = __float_as_int(static_cast<float>(c - static_cast<double>(tb0[d])));
     }
@@ -480,14 +499,19 @@ __global__ void __launch_bounds__(kBrThreads, 4)
     uint32_t todo = 0;  // bit k: voxel k is not strictly interior -> handled after the hot loop
     float* __restrict__ o = out;
 
-    if (ORDER == 1 && nz == kBrTZ) {
-      // ---- column fast path (order 1, full-depth tile): see brick_column_linear
+    if (ORDER == 1 && (SCRUB || sizeof(T) == 2 || (nz == kBrTZ && g.TZ == kBrTZ))) {
+      // ---- column fast path (order 1): see brick_column_packed / brick_column_linear
       const BrickCol cc{brick, plane_b, row_b, out_plane, u0[0], u0[1], u0[2], mcol[0][0], mcol[1][0],
                         mcol[2][0]};
       uint32_t rest;
-      if (SCRUB || sizeof(T) == 2) {  // finite taps: packed arithmetic
-        rest = tile_in ? brick_column_packed<T, false, LY>(cc, mid, half, out)
-                       : brick_column_packed<T, true, LY>(cc, mid, half, out);
+      if (SCRUB || sizeof(T) == 2) {  // finite taps: packed arithmetic, any tile depth
+        if (!LY && g.TZ == kBrTZMax) {
+          rest = tile_in ? brick_column_packed<T, false, LY, kBrTZMax>(cc, mid, half, out, nz)
+                         : brick_column_packed<T, true, LY, kBrTZMax>(cc, mid, half, out, nz);
+        } else {
+          rest = tile_in ? brick_column_packed<T, false, LY, kBrTZ>(cc, mid, half, out, nz)
+                         : brick_column_packed<T, true, LY, kBrTZ>(cc, mid, half, out, nz);
+        }
       } else if (tile_in) {
         rest = brick_column_linear<T, SCRUB, false, LY>(cc, mid, half, out);
       } else {
@@ -505,7 +529,7 @@ __global__ void __launch_bounds__(kBrThreads, 4)
                              dx > half[2] + 0.5f + kEdge;
         const float v = outside ? 0.0f
                                 : brick_sample_exact<T, ORDER, BOUNDARY, SCRUB>(
-                                      p, brick, b0[0], b0[1], b0[2], g.BY, g.BX, z0 + k, y, x);
+                                      p, brick, b0[0], b0[1], b0[2], g.BZ, g.BY, g.BX, z0 + k, y, x);
         brick_put<LY>(out + k * out_plane, v);
       }
       continue;
@@ -577,7 +601,7 @@ __global__ void __launch_bounds__(kBrThreads, 4)
                            dx > half[2] + 0.5f + kEdge;
       const float v = outside ? 0.0f
                               : brick_sample_exact<T, ORDER, BOUNDARY, SCRUB>(
-                                    p, brick, b0[0], b0[1], b0[2], g.BY, g.BX, z0 + k, y, x);
+                                    p, brick, b0[0], b0[1], b0[2], g.BZ, g.BY, g.BX, z0 + k, y, x);
       brick_put<LY>(out + k * out_plane, v);
     }
   }
@@ -597,12 +621,11 @@ __global__ void __launch_bounds__(kBrThreads, 4)
 // host side
 // ---------------------------------------------------------------------------------------------
 template <typename T>
-static bool brick_geometry(const AffineParams& p, bool ly, BrickGeom* g, size_t* smem_bytes) {
+static bool brick_geometry_tz(const AffineParams& p, bool ly, int tz, int64_t max_bytes, BrickGeom* g,
+                              size_t* smem_bytes) {
   const int kBrTY = ly ? kBrLanes : kBrOther, kBrTX = ly ? kBrOther : kBrLanes;
-  if (reinterpret_cast<uintptr_t>(p.src) % 16 != 0) return false;
-  if ((static_cast<int64_t>(p.spitch) * sizeof(T)) % 16 != 0) return false;
   const int vec = 16 / sizeof(T);
-  const int t[3] = {kBrTZ - 1, kBrTY - 1, kBrTX - 1};
+  const int t[3] = {tz - 1, kBrTY - 1, kBrTX - 1};
   int ext[3];
   for (int d = 0; d < 3; ++d) {
     double neg = 0.0, pos = 0.0;
@@ -612,10 +635,30 @@ static bool brick_geometry(const AffineParams& p, bool ly, BrickGeom* g, size_t*
     }
     const double e = pos - neg;
     if (!(e < 240.0)) return false;
-    ext[d] = static_cast<int>(e) + 5;
+    // taps floor(c_min - guard) .. floor(c_max + guard) + 1:  at most int(e + 2 guard) + 3 of them
+    ext[d] = static_cast<int>(e + 2.0 * kBrGuard) + 3;
     g->neg[d] = neg;
     g->pos[d] = pos;
   }
+  int BX = ext[2] + (vec - 1);  // the brick origin is rounded down to 16 bytes
+  BX = (BX + vec - 1) / vec * vec;
+  if (ext[0] > 256 || ext[1] > 256 || BX > 256) return false;
+  const int64_t bytes = static_cast<int64_t>(ext[0]) * ext[1] * BX * sizeof(T);
+  if (bytes > max_bytes) return false;
+  g->TZ = tz;
+  g->BZ = ext[0];
+  g->BY = ext[1];
+  g->BX = BX;
+  g->bytes = static_cast<int>(bytes);
+  *smem_bytes = static_cast<size_t>(bytes) + 256 + (ly ? kBrStageBytes : 0);
+  return true;
+}
+
+template <typename T>
+static bool brick_geometry(const AffineParams& p, bool ly, bool finite_taps, BrickGeom* g,
+                           size_t* smem_bytes) {
+  if (reinterpret_cast<uintptr_t>(p.src) % 16 != 0) return false;
+  if ((static_cast<int64_t>(p.spitch) * sizeof(T)) % 16 != 0) return false;
   for (int i = 0; i < 9; ++i) g->mcol[i] = static_cast<float>(p.m[4 * (i / 3) + (i % 3)]);
   // |coordinate| bound over the whole output (keeps the device-side int conversions defined)
   for (int d = 0; d < 3; ++d) {
@@ -624,17 +667,13 @@ static bool brick_geometry(const AffineParams& p, bool ly, BrickGeom* g, size_t*
                          fabs(p.m[4 * d + 2]) * (p.ox + fabs((double)p.cx)) + fabs(p.m[4 * d + 3]);
     if (!(reach < 1.0e9)) return false;
   }
-  int BX = ext[2] + (vec - 1);
-  BX = (BX + vec - 1) / vec * vec;
-  if (ext[0] > 256 || ext[1] > 256 || BX > 256) return false;
-  const int64_t bytes = static_cast<int64_t>(ext[0]) * ext[1] * BX * sizeof(T);
-  if (bytes > 72 * 1024) return false;  // keep >= 3 CTAs per SM; larger footprints use the gather path
-  g->BZ = ext[0];
-  g->BY = ext[1];
-  g->BX = BX;
-  g->bytes = static_cast<int>(bytes);
-  *smem_bytes = static_cast<size_t>(bytes) + 256 + (ly ? kBrStageBytes : 0);
-  return true;
+  // deep tiles when the output is deep enough to fill them and the brick still leaves 3 CTAs/SM
+  // (3 x 74 KB + static shared memory < 227 KB); else 8-deep tiles, >= 3 CTAs/SM as well; larger
+  // footprints use the gather path
+  if (!ly && finite_taps && p.order == 1 && p.oz > kBrTZ &&
+      brick_geometry_tz<T>(p, ly, kBrTZMax, 74 * 1024, g, smem_bytes))
+    return true;
+  return brick_geometry_tz<T>(p, ly, kBrTZ, 72 * 1024, g, smem_bytes);
 }
 
 template <typename T, int ORDER, int BOUNDARY, bool SCRUB, bool LY>
@@ -664,7 +703,7 @@ static int launch_brick(const AffineParams& p, const BrickGeom& g, size_t smem_b
     return B2_ERR_UNSUPPORTED;
   }
   constexpr int kBrTY = LY ? kBrLanes : kBrOther, kBrTX = LY ? kBrOther : kBrLanes;
-  const int tiles_z = (p.oz + kBrTZ - 1) / kBrTZ;
+  const int tiles_z = (p.oz + g.TZ - 1) / g.TZ;
   const int tiles_y = (p.oy + kBrTY - 1) / kBrTY;
   const int tiles_x = (p.ox + kBrTX - 1) / kBrTX;
   const int64_t tiles = static_cast<int64_t>(tiles_z) * tiles_y * tiles_x;
@@ -684,9 +723,9 @@ template <typename T, bool LY>
 static int brick_typed_ly(const AffineParams& p, cudaStream_t stream, bool* eligible) {
   BrickGeom g{};
   size_t smem = 0;
-  *eligible = brick_geometry<T>(p, LY, &g, &smem);
-  if (!*eligible) return B2_ERR_UNSUPPORTED;
   const bool scrub = p.scrub && sizeof(T) == 4;
+  *eligible = brick_geometry<T>(p, LY, scrub || sizeof(T) == 2, &g, &smem);
+  if (!*eligible) return B2_ERR_UNSUPPORTED;
 #define B2_BR(ORD, BND)                                            \
   (scrub ? launch_brick<T, ORD, BND, true, LY>(p, g, smem, stream) \
          : launch_brick<T, ORD, BND, false, LY>(p, g, smem, stream))

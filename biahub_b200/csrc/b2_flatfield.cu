@@ -22,6 +22,7 @@
 // mean(pattern): every partial sum of half-integers below 2^52 is exact, so the integer sum equals
 // numpy's pairwise float64 sum bit for bit (tests/test_flatfield_oracle.py).
 #include <algorithm>
+#include <type_traits>
 
 #include "b2_common.cuh"
 
@@ -65,9 +66,10 @@ __global__ void __launch_bounds__(kFfThreads)
   int krem[kFfPix] = {k1, k1, k1, k1};     // rank within the samples matching the prefix
   int ceq[kFfPix] = {0, 0, 0, 0};          // after the last pass: samples equal to the median
 
-  auto load4 = [&](int z, uint32_t (&v)[kFfPix]) {
+  // VEC: the thread's 4 pixels are one aligned 8-byte load per plane (CTA-interior, P % 4 == 0)
+  auto load4 = [&](auto vec_tag, int z, uint32_t (&v)[kFfPix]) {
     const uint16_t* q = p.src + static_cast<int64_t>(z) * p.P + pix;
-    if (vec) {
+    if (decltype(vec_tag)::value) {
       const uint2 w = __ldg(reinterpret_cast<const uint2*>(q));
       v[0] = w.x & 0xffffu; v[1] = w.x >> 16; v[2] = w.y & 0xffffu; v[3] = w.y >> 16;
     } else {
@@ -86,32 +88,55 @@ __global__ void __launch_bounds__(kFfThreads)
       for (uint32_t j = 0; j < kFfPix; ++j)
         asm volatile("st.shared.u16 [%0], %1;" ::"r"(hbase + ff_slot(b, j, t)), "h"((unsigned short)0));
     if (npx > 0) {
-#pragma unroll 4
-      for (int z = 0; z < p.Z; ++z) {
-        uint32_t v[kFfPix];
-        load4(z, v);
-        // the four pixels own separate counters: their four loads are issued before the four
-        // stores (pixel order ld, add, st, ld, ... would chain the shared-memory round trips);
-        // measured gain 3 %: the kernel stays latency-bound at ~35 % of its issue slots
-        uint32_t addr[kFfPix];
-        bool on[kFfPix];
-        unsigned short cnt[kFfPix];
+      auto histogram_pass = [&](auto vec_tag) {
+      // kFfAhead planes are loaded before their counters are touched: the counter updates are an
+      // ordered chain of shared-memory round trips (two samples of a column may hit the same
+      // bin), so without this the kernel waits for one global load at a time per thread
+      // (measured: 25 % of the HBM bandwidth, 35 % of the issue slots)
+      constexpr int kFfAhead = 8;
+      for (int zb = 0; zb < p.Z; zb += kFfAhead) {
+        uint32_t vv[kFfAhead][kFfPix];
 #pragma unroll
-        for (uint32_t j = 0; j < kFfPix; ++j) {
-          const uint32_t hi = pass == 0 ? 0u : (v[j] >> (shift + 4));
-          on[j] = hi == prefix[j];
-          addr[j] = hbase + ff_slot((v[j] >> shift) & 15u, j, t);
+        for (int u = 0; u < kFfAhead; ++u) {
+          if (zb + u < p.Z) {
+            load4(vec_tag, zb + u, vv[u]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < kFfPix; ++j) vv[u][j] = 0u;
+          }
         }
 #pragma unroll
-        for (uint32_t j = 0; j < kFfPix; ++j) {
-          cnt[j] = 0;
-          if (on[j]) asm volatile("ld.shared.u16 %0, [%1];" : "=h"(cnt[j]) : "r"(addr[j]));
-        }
+        for (int u = 0; u < kFfAhead; ++u) {
+          if (zb + u >= p.Z) break;
+          uint32_t (&v)[kFfPix] = vv[u];
+          // the four pixels own separate counters: their four loads are issued before the four
+          // stores (pixel order ld, add, st, ld, ... would chain the shared-memory round trips)
+          uint32_t addr[kFfPix];
+          bool on[kFfPix];
+          unsigned short cnt[kFfPix];
 #pragma unroll
-        for (uint32_t j = 0; j < kFfPix; ++j) {
-          const unsigned short c = static_cast<unsigned short>(cnt[j] + 1);
-          if (on[j]) asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr[j]), "h"(c));
+          for (uint32_t j = 0; j < kFfPix; ++j) {
+            const uint32_t hi = pass == 0 ? 0u : (v[j] >> (shift + 4));
+            on[j] = hi == prefix[j];
+            addr[j] = hbase + ff_slot((v[j] >> shift) & 15u, j, t);
+          }
+#pragma unroll
+          for (uint32_t j = 0; j < kFfPix; ++j) {
+            cnt[j] = 0;
+            if (on[j]) asm volatile("ld.shared.u16 %0, [%1];" : "=h"(cnt[j]) : "r"(addr[j]));
+          }
+#pragma unroll
+          for (uint32_t j = 0; j < kFfPix; ++j) {
+            const unsigned short c = static_cast<unsigned short>(cnt[j] + 1);
+            if (on[j]) asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr[j]), "h"(c));
+          }
         }
+      }
+      };
+      if (vec) {
+        histogram_pass(std::true_type{});
+      } else {
+        histogram_pass(std::false_type{});
       }
       // scan: the bin where the cumulative count passes the rank
 #pragma unroll
@@ -152,12 +177,20 @@ __global__ void __launch_bounds__(kFfThreads)
     }
   }
   if (need_next) {
-    for (int z = 0; z < p.Z; ++z) {
-      uint32_t v[kFfPix];
-      load4(z, v);
+    auto next_pass = [&](auto vec_tag) {
+#pragma unroll 8
+      for (int z = 0; z < p.Z; ++z) {
+        uint32_t v[kFfPix];
+        load4(vec_tag, z, v);
 #pragma unroll
-      for (int j = 0; j < kFfPix; ++j)
-        if (v[j] > prefix[j] && m2[j] != prefix[j]) m2[j] = min(m2[j], v[j]);
+        for (int j = 0; j < kFfPix; ++j)
+          if (v[j] > prefix[j] && m2[j] != prefix[j]) m2[j] = min(m2[j], v[j]);
+      }
+    };
+    if (vec) {
+      next_pass(std::true_type{});
+    } else {
+      next_pass(std::false_type{});
     }
   }
   unsigned long long local = 0ull;

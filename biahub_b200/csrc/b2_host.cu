@@ -533,7 +533,10 @@ int host_affine(const void* h_src, int src_dtype, int64_t sz, int64_t sy, int64_
   const int64_t c0[3] = {crop_start ? crop_start[0] : 0, crop_start ? crop_start[1] : 0,
                          crop_start ? crop_start[2] : 0};
   const size_t plane_out = static_cast<size_t>(oy) * ox * sizeof(float);
-  const int64_t per_slab = std::max<int64_t>(1, static_cast<int64_t>(kSlabBytes / plane_out));
+  // whole 16-plane tile layers of the generic warp kernel per slab (its bricks are staged per
+  // 16-deep tile: a 2-plane slab would stage them for 2 planes each)
+  int64_t per_slab = std::max<int64_t>(1, static_cast<int64_t>(kSlabBytes / plane_out));
+  per_slab = (per_slab + 15) / 16 * 16;
   std::vector<Slab> slabs;
   void* d_src = c->d_src;
   std::vector<double> M(M12, M12 + 12);

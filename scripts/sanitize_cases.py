@@ -1,0 +1,128 @@
+#!/usr/bin/env python
+"""One small case per kernel family, for compute-sanitizer:
+
+    compute-sanitizer --tool memcheck  python scripts/sanitize_cases.py
+    compute-sanitizer --tool racecheck python scripts/sanitize_cases.py
+    compute-sanitizer --tool synccheck python scripts/sanitize_cases.py
+
+(one tool per gpurun call, see /opt/skills/guides/B200_PROFILING.md).  Every case is also checked
+against the oracle, so a run that passes the tool but computes garbage still fails.  The families:
+deskew TMA register kernel (u16 N=3, f32), deskew staging kernel (u16 N=1), deskew manual brick
+fill (unaligned rows), deskew gather; zsep X / LY / integer shift; brick X / LY / order 0; affine
+gather; overhang fill (cube + cross) and slice averaging; flat-field; cubic spline; the host
+pipelines (slab ring, chained unit, fill).
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+import biahub_b200 as b2  # noqa: E402
+from biahub_b200 import _cabi  # noqa: E402
+from oracle import affine_oracle as ao  # noqa: E402
+from oracle import deskew_oracle as do  # noqa: E402
+from oracle import flatfield_oracle as fo  # noqa: E402
+
+rng = np.random.default_rng(0)
+done = []
+
+
+def cuda(a):
+    if a.dtype == np.uint16:
+        return torch.from_numpy(a.view(np.int16)).cuda().view(torch.uint16)
+    return torch.from_numpy(a).cuda()
+
+
+def check(name, got, want, tol):
+    got = got.cpu().numpy() if hasattr(got, "cpu") else got
+    err = float(np.abs(got.astype(np.float64) - want).max()) if want.size else 0.0
+    assert got.shape == want.shape and err <= tol, (name, got.shape, want.shape, err)
+    done.append(name)
+
+
+# ---- deskew ---------------------------------------------------------------------------------
+u = rng.integers(0, 65536, size=(96, 30, 128), dtype=np.uint16)
+f = (rng.random((96, 12, 64), dtype=np.float32) * 4095).astype(np.float32)
+for n, path in ((3, _cabi.PATH_TMA), (1, _cabi.PATH_TMA), (2, _cabi.PATH_TMA), (3, _cabi.PATH_GATHER)):
+    check(f"deskew u16 N={n} path={path}", b2.fast_deskew_zyx(cuda(u), 30.0, 0.386, False, n, _path=path),
+          do.deskew_oracle_numpy(u, 30.0, 0.386, False, n), 2e-7 * 65535)
+check("deskew f32 N=3 keep", b2.fast_deskew_zyx(cuda(f), 30.0, 0.386, True, 3, _path=_cabi.PATH_TMA),
+      do.deskew_oracle_numpy(f, 30.0, 0.386, True, 3), 2e-7 * 4095)
+un = rng.integers(0, 65536, size=(96, 9, 70), dtype=np.uint16)   # rows not 16-byte aligned
+check("deskew u16 unaligned rows (manual brick fill)", b2.fast_deskew_zyx(cuda(un), 30.0, 0.386, False, 3),
+      do.deskew_oracle_numpy(un, 30.0, 0.386, False, 3), 2e-7 * 65535)
+
+# ---- overhang fill, legacy averaging -------------------------------------------------------
+base = do.deskew_oracle_numpy(u, 30.0, 0.386, True, 3)
+check("fill cube mean", b2.fast_deskew_zyx(cuda(u), 30.0, 0.386, True, 3, overhang_fill="mean"),
+      do.fill_overhang_oracle(base, None)[0], 1e-5 * 65535)
+check("fill cube const", b2.fast_deskew_zyx(cuda(u), 30.0, 0.386, True, 3, overhang_fill=77.0),
+      do.fill_overhang_oracle(base, 77.0)[0], 1e-5 * 65535)
+check("legacy deskew_zyx (average kernel + cross fill)", b2.deskew_zyx(u, 30.0, 0.386, True, average_n_slices=4,
+                                                                     overhang_fill="mean"),
+      do.deskew_legacy_oracle(u, 30.0, 0.386, True, 4, "mean"), 1e-5 * 65535)
+
+# ---- affine: zsep X, zsep LY, integer shift, brick X, brick LY, gather -----------------------
+shape = (12, 96, 160)
+vol = (rng.random(shape, dtype=np.float32) * 4095).astype(np.float32)
+vol[3, 4, 5] = np.nan
+t = cuda(vol)
+c3 = ao.register_matrix_c3(shape)
+rot90 = b2.get_3D_rotation_matrix(shape, 90)
+out90 = (12, 160, 96)
+tilt = np.eye(4)
+a, b = np.radians(1.5), np.radians(-0.8)
+R = (np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]])
+     @ np.array([[np.cos(b), -np.sin(b), 0], [np.sin(b), np.cos(b), 0], [0, 0, 1]]))
+ctr = (np.array(shape) - 1) / 2
+tilt[:3, :3] = R
+tilt[:3, 3] = ctr - R @ ctr
+shift = np.eye(4)
+shift[:3, 3] = (1, -2, 3)
+cases = [("zsep X", c3, shape), ("zsep LY", rot90, out90), ("integer shift", shift, shape),
+         ("brick X", c3 @ tilt, shape), ("brick LY", rot90 @ tilt, out90)]
+for name, M, oshape in cases:
+    for order in (1, 0):
+        want = ao.affine_oracle_numpy(vol, M, oshape, order, "itk")
+        got = b2.affine_warp(t, M, oshape, order=order, boundary="itk", _path=_cabi.PATH_TMA)
+        check(f"{name} order {order}", got, want, 0.0 if order == 0 else 1e-4 * 4095)
+check("affine gather", b2.affine_warp(t, c3 @ tilt, shape, order=1, boundary="constant", _path=_cabi.PATH_GATHER),
+      ao.affine_oracle_numpy(vol, c3 @ tilt, shape, 1, "constant"), 1e-4 * 4095)
+u16v = rng.integers(0, 65536, size=shape, dtype=np.uint16)
+check("brick X uint16", b2.affine_warp(cuda(u16v), c3 @ tilt, shape, order=1, boundary="itk", _path=_cabi.PATH_TMA),
+      ao.affine_oracle_numpy(u16v, c3 @ tilt, shape, 1, "itk"), 1e-4 * 65535)
+
+# ---- cubic spline (method="scipy") ----------------------------------------------------------
+sv = np.nan_to_num(vol, nan=0)
+check("spline3 f32", b2.spline_warp(cuda(sv), c3 @ tilt), ao.affine_oracle_spline3(sv, c3 @ tilt), 1e-4 * 4095)
+
+# ---- flat-field -----------------------------------------------------------------------------
+cam = (100 + rng.poisson(30, size=(24, 20, 64))).astype(np.uint16)
+check("flat-field", b2._flat_field_czyx(cam[None], [0]), fo.flat_field_czyx_oracle(cam[None], [0]), 0.0)
+
+# ---- host pipelines (pinned rings, slab ring, three streams) ---------------------------------
+check("b2h_deskew", b2._fast_deskew_czyx(u[None], ls_angle_deg=30.0, px_to_scan_ratio=0.386, keep_overhang=False,
+                                         average_n_slices=3)[0],
+      do.deskew_oracle_numpy(u, 30.0, 0.386, False, 3), 2e-7 * 65535)
+check("b2h_deskew_fill", b2._fast_deskew_czyx(u[None], ls_angle_deg=30.0, px_to_scan_ratio=0.386, keep_overhang=True,
+                                              average_n_slices=3, overhang_fill="mean")[0],
+      do.fill_overhang_oracle(base, None)[0], 1e-5 * 65535)
+check("b2h_affine3d", b2.apply_affine_transform(vol, c3 @ tilt, shape),
+      ao.affine_oracle_numpy(vol, c3 @ tilt, shape, 1, "itk"), 1e-4 * 4095)
+check("b2h_affine3d_spline3", b2.apply_affine_transform(sv, c3, shape, method="scipy"),
+      ao.affine_oracle_spline3(sv, c3), 1e-4 * 4095)
+mid = do.deskew_oracle_numpy(u, 30.0, 0.386, False, 3)
+Mm = ao.register_matrix_c3(mid.shape)
+check("b2h_deskew_affine3d", b2.deskew_then_register(u, Mm, mid.shape, ls_angle_deg=30.0, px_to_scan_ratio=0.386,
+                                                     keep_overhang=False, average_n_slices=3),
+      ao.affine_oracle_numpy(mid, Mm, mid.shape, 1, "itk"), 1e-4 * 65535)
+torch.cuda.synchronize()
+_cabi.lib().b2h_release()
+print(f"sanitize_cases: {len(done)} cases ok, {_cabi.launch_count()} kernel launches")
+for name in done:
+    print("  ok ", name)

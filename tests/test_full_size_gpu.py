@@ -111,3 +111,84 @@ def test_c4_stabilize_full_size_integer_and_fractional():
     # device API returns the same bits as the host pipeline
     dev = apply_stabilization_transform(torch.from_numpy(vol).cuda(), mats, 2).cpu().numpy()
     assert np.array_equal(dev, out)
+
+
+def test_c2_variants_full_size_keep_overhang_and_production_ratio():
+    """configs[1] variants: keep_overhang=True (X_out 2333) and the production pixel ratio 0.755
+    (nextflow/configs/*/deskew.yml: 0.1133 / 0.150 → (100,2048,800)); TMA kernel against the gather
+    kernel bit for bit and against the sampled-voxel oracle."""
+    import torch
+
+    import biahub_b200 as b2
+    from biahub_b200 import _cabi
+
+    rng = np.random.default_rng(1001)
+    raw = rng.integers(0, 65536, size=(800, 300, 2048), dtype=np.uint16)
+    t = _to_cuda(raw)
+    for px, keep, shape in ((0.386, True, (100, 2048, 2333)), (0.755, False, (100, 2048, 800))):
+        a = b2.fast_deskew_zyx(t, 30.0, px, keep, 3, _path=_cabi.PATH_TMA)
+        assert tuple(a.shape) == shape == b2.get_deskewed_data_shape(raw.shape, 30.0, px, keep, 3)[0]
+        g = b2.fast_deskew_zyx(t, 30.0, px, keep, 3, _path=_cabi.PATH_GATHER)
+        assert torch.equal(a, g)
+        del g
+        a_h = a.cpu().numpy()
+        pts = _sample_points(shape, 40000, 11)
+        want = do.deskew_oracle_points(raw, 30.0, px, keep, 3, pts)
+        assert np.abs(a_h[pts[:, 0], pts[:, 1], pts[:, 2]] - want).max() <= 2e-7 * 65535.0
+        del a, a_h
+    # keep_overhang + overhang_fill through the pipelined host path at full size: no zero is left
+    # and the un-masked voxels are untouched
+    filled = b2._fast_deskew_czyx(raw[None], ls_angle_deg=30.0, px_to_scan_ratio=0.386,
+                                  keep_overhang=True, average_n_slices=3, overhang_fill="mean")[0]
+    plain = b2._fast_deskew_czyx(raw[None], ls_angle_deg=30.0, px_to_scan_ratio=0.386,
+                                 keep_overhang=True, average_n_slices=3)[0]
+    assert filled.shape == (100, 2048, 2333) and (filled == 0).sum() == 0
+    changed = filled != plain
+    assert changed.any() and np.unique(filled[changed]).size == 1      # one fill value
+    assert abs(float(filled[changed][0]) - float(plain[~changed].mean(dtype=np.float64))) <= 1e-2
+
+
+def test_c5_chained_unit_full_size():
+    """configs[4] unit at full size: deskew uint16 (800,300,2048) N=3 → register the float32
+    (100,2048,1813) result with the C3-style matrix; the one pipelined host call
+    (b2h_deskew_affine3d) equals the device chain bit for bit, and sampled voxels match the oracle
+    chain (oracle deskew at the taps' source voxels → oracle warp)."""
+    import torch
+
+    import biahub_b200 as b2
+
+    rng = np.random.default_rng(4000)
+    raw = rng.integers(0, 65536, size=(800, 300, 2048), dtype=np.uint16)
+    kw = dict(ls_angle_deg=30.0, px_to_scan_ratio=0.386, keep_overhang=False, average_n_slices=3)
+    mid_shape = (100, 2048, 1813)
+    M = ao.register_matrix_c3(mid_shape)
+    host = b2.deskew_then_register(raw, M, mid_shape, **kw)
+    dev = b2.deskew_then_register(_to_cuda(raw), M, mid_shape, **kw)
+    assert tuple(dev.shape) == mid_shape
+    assert np.array_equal(dev.cpu().numpy(), host)
+    # two-step product path (what the two CLI commands do): the dense 1813-float rows are not
+    # 16-byte aligned, so the warp runs on the gather kernel instead of the TMA kernel the
+    # pitched chain uses — same arithmetic, float64 vs tile-local fp32 coordinates
+    mid = b2.fast_deskew_zyx(_to_cuda(raw), 30.0, 0.386, False, 3)
+    two = b2.affine_warp(mid, M, mid_shape, order=1, boundary="itk")
+    assert float((two - dev).abs().max()) <= 1e-4 * 65535.0
+    del two, mid
+    # oracle chain on sampled output voxels: the 8 taps of each sample come from the oracle deskew
+    pts = _sample_points(mid_shape, 20000, 13)
+    A, tr = M[:3, :3], M[:3, 3]
+    c = pts @ A.T + tr
+    base = np.floor(c).astype(np.int64)
+    need = set()
+    for dz in (0, 1):
+        for dy in (0, 1):
+            for dx in (0, 1):
+                q = base + np.array([dz, dy, dx])
+                ok = np.all((q >= 0) & (q < np.array(mid_shape)), axis=1)
+                need.update(map(tuple, q[ok]))
+    need = np.array(sorted(need))
+    vals = do.deskew_oracle_points(raw, 30.0, 0.386, False, 3, need)
+    sparse = np.zeros(mid_shape, dtype=np.float32)          # only the needed taps are filled in
+    sparse[need[:, 0], need[:, 1], need[:, 2]] = vals
+    want = ao.affine_oracle_points(sparse, M, pts, 1, "itk")
+    got = host[pts[:, 0], pts[:, 1], pts[:, 2]]
+    assert np.abs(got.astype(np.float64) - want).max() <= 1e-4 * 65535.0
