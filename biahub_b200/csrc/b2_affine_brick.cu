@@ -12,6 +12,9 @@
 // (volume border, ITK half-voxel band, the k+0.5 rounding point of nearest-neighbour) is
 // re-evaluated exactly in float64 through `resolve_axis`, so inside/outside and nearest-neighbour
 // index decisions are identical to the float64 oracle (order 0 stays bit-exact).
+#include <algorithm>
+#include <cstdlib>
+
 #include "b2_affine.cuh"
 
 namespace b2 {
@@ -292,7 +295,7 @@ __device__ __forceinline__ void brick_quad_moved<uint16_t>(uint32_t a, uint32_t 
 // static) and only the upper plane is loaded — the lower one again only when the (y, x) cell moved.
 // Per voxel: 2 coordinate adds, 3 floors, 5 weight ops (y and x packed), 3 address, 1 compare,
 // 4 + 4 predicated LDS, 8 lerp instructions (3 FADD2 + 3 FFMA2 + 2 scalar), check + store.
-template <typename T, bool CHECK, bool LY, int TZ>
+template <typename T, bool CHECK, bool LY, int TZ, int BOUNDARY>
 __device__ __forceinline__ uint32_t brick_column_packed(const BrickCol& c, const float (&mid)[3],
                                                         const float (&half)[3],
                                                         float* __restrict__ out, const int nz) {
@@ -315,17 +318,31 @@ __device__ __forceinline__ uint32_t brick_column_packed(const BrickCol& c, const
 #pragma unroll
   for (int k = 0; k < TZ; ++k) {
     bool interior = true;
+    float cz = uz;       // the coordinate this voxel samples at (clamped in the ITK band)
+    f32x2 cyx = uyx;
     if (CHECK) {
       float uy, ux;
       upk2(uyx, uy, ux);
-      interior = fabsf(uz - mid[0]) <= half[0] - kEdge && fabsf(uy - mid[1]) <= half[1] - kEdge &&
-                 fabsf(ux - mid[2]) <= half[2] - kEdge;
+      if (BOUNDARY == B2_BOUNDARY_ITK) {
+        // ITK: inside iff -0.5 <= c < n - 0.5, and inside the half-voxel band the interpolator
+        // clamps to the edge voxel (base clamped, neighbour dropped) = trilinear at the CLAMPED
+        // coordinate, continuous across c = 0 and c = n-1: only the +-0.5 edges are decisions
+        interior = fabsf(uz - mid[0]) <= half[0] + 0.5f - kEdge &&
+                   fabsf(uy - mid[1]) <= half[1] + 0.5f - kEdge &&
+                   fabsf(ux - mid[2]) <= half[2] + 0.5f - kEdge;
+        cz = fminf(fmaxf(uz, mid[0] - half[0]), mid[0] + half[0]);
+        cyx = pk2(fminf(fmaxf(uy, mid[1] - half[1]), mid[1] + half[1]),
+                  fminf(fmaxf(ux, mid[2] - half[2]), mid[2] + half[2]));
+      } else {
+        interior = fabsf(uz - mid[0]) <= half[0] - kEdge && fabsf(uy - mid[1]) <= half[1] - kEdge &&
+                   fabsf(ux - mid[2]) <= half[2] - kEdge;
+      }
     }
     if (interior) {
-      const float tz = __fadd_rd(uz, kMagic);
-      const f32x2 tyx = add2_rd(uyx, magic2);
-      const float wz = uz - (tz - kMagic);
-      const f32x2 wyx = sub2(uyx, sub2(tyx, magic2));
+      const float tz = __fadd_rd(cz, kMagic);
+      const f32x2 tyx = add2_rd(cyx, magic2);
+      const float wz = cz - (tz - kMagic);
+      const f32x2 wyx = sub2(cyx, sub2(tyx, magic2));
       float ty, tx, wy, wx;
       upk2(tyx, ty, tx);
       upk2(wyx, wy, wx);
@@ -506,11 +523,11 @@ __global__ void __launch_bounds__(kBrThreads, 4)
       uint32_t rest;
       if (SCRUB || sizeof(T) == 2) {  // finite taps: packed arithmetic, any tile depth
         if (!LY && g.TZ == kBrTZMax) {
-          rest = tile_in ? brick_column_packed<T, false, LY, kBrTZMax>(cc, mid, half, out, nz)
-                         : brick_column_packed<T, true, LY, kBrTZMax>(cc, mid, half, out, nz);
+          rest = tile_in ? brick_column_packed<T, false, LY, kBrTZMax, BOUNDARY>(cc, mid, half, out, nz)
+                         : brick_column_packed<T, true, LY, kBrTZMax, BOUNDARY>(cc, mid, half, out, nz);
         } else {
-          rest = tile_in ? brick_column_packed<T, false, LY, kBrTZ>(cc, mid, half, out, nz)
-                         : brick_column_packed<T, true, LY, kBrTZ>(cc, mid, half, out, nz);
+          rest = tile_in ? brick_column_packed<T, false, LY, kBrTZ, BOUNDARY>(cc, mid, half, out, nz)
+                         : brick_column_packed<T, true, LY, kBrTZ, BOUNDARY>(cc, mid, half, out, nz);
         }
       } else if (tile_in) {
         rest = brick_column_linear<T, SCRUB, false, LY>(cc, mid, half, out);
@@ -618,6 +635,174 @@ __global__ void __launch_bounds__(kBrThreads, 4)
 }
 
 // ---------------------------------------------------------------------------------------------
+// Persistent, double-buffered form of the kernel above for the production case (order 1, finite
+// taps, lanes along x).  The one-tile-per-CTA kernel spends 20-27 % of its resident warp time in
+// the mbarrier wait at the start of each tile (ncu source page: the `try_wait` branch) and ~10 %
+// of its instructions in per-CTA set-up.  Here a CTA (8 consumer warps + 1 producer warp, 2 CTAs
+// per SM) walks a strided sequence of tiles with TWO brick buffers: while the consumers work on
+// tile i from one buffer, the producer evaluates the geometry of tile i+1 (float64, tile decode
+// included) and has its TMA box load in flight into the other one; one CTA barrier per tile hands
+// the buffers over.  Loop-invariant set-up (matrix columns, strides, lane coordinates) is done
+// once per CTA.
+// ---------------------------------------------------------------------------------------------
+constexpr int kBpConsumers = kBrThreads;        // 16 (y) x 32 (x) x kBrTZ tile, two columns per thread
+constexpr int kBpThreads = kBpConsumers + 32;   // + the producer warp
+
+template <typename T, int BOUNDARY>
+__global__ void __maxnreg__(112)  // 2 CTAs/SM: 2 x 288 threads x 112 registers <= 64 K
+    affine_brick_pers_kernel(const __grid_constant__ CUtensorMap src_map,
+                             const __grid_constant__ AffineParams p,
+                             const __grid_constant__ BrickGeom g, const int tiles_z,
+                             const int tiles_x, const int tiles_total) {
+  constexpr bool SCRUB = sizeof(T) == 4;  // float32 taps are scrubbed on the exact path
+  constexpr int kVec = 16 / static_cast<int>(sizeof(T));
+  constexpr int kTY = kBrOther, kTX = kBrLanes;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t bar[2];
+  // per buffer: b0[3], bits(c0l[3]), flags (1 brick ok, 2 interior, 4 outside, 8 load issued), z0, y0, x0
+  __shared__ int s_geo[2][12];
+  uint8_t* smem_al = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
+  const uint32_t brick_stride = static_cast<uint32_t>((g.bytes + 127) / 128) * 128u;
+  const uint32_t brick_base = smem_u32(smem_al);
+  const bool producer = threadIdx.x >= kBpConsumers;
+
+  // geometry of `tile` into buffer `slot` + its TMA load (one thread of the producer warp)
+  auto plan = [&](int tile, int slot) {
+    const int tz_i = tile % tiles_z;
+    const int tx_i = (tile / tiles_z) % tiles_x;
+    const int ty_i = tile / (tiles_z * tiles_x);
+    const int z0 = tz_i * kBrTZ, y0 = ty_i * kTY, x0 = tx_i * kTX;
+    int tb0[3], tbhi[3];
+    const double zf = static_cast<double>(z0 + p.cz), yf = static_cast<double>(y0 + p.cy),
+                 xf = static_cast<double>(x0 + p.cx);
+    const int n[3] = {p.sz, p.sy, p.sx};
+    bool inside = true, outside = false;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const double c = coord_full(p.m + 4 * d, zf, yf, xf);
+      tb0[d] = __double2int_rd(c + (g.neg[d] - kBrGuard));
+      outside = outside || tb0[d] >= n[d] + 1 || __double2int_rd(c + (g.pos[d] + kBrGuard)) <= -2;
+      inside = inside && tb0[d] >= 1;
+      if (d == 2) tb0[d] &= ~(kVec - 1);  // innermost TMA coordinate must be 16-byte aligned
+      tbhi[d] = __double2int_rd(c + (g.pos[d] + kBrGuard)) + 1;  // index of the last tap
+      inside = inside && tbhi[d] <= n[d] - 2;
+      s_geo[slot][d] = tb0[d];
+      s_geo[slot][3 + d] = __float_as_int(static_cast<float>(c - static_cast<double>(tb0[d])));
+    }
+    const bool ok = (tbhi[0] - tb0[0]) < g.BZ && (tbhi[1] - tb0[1]) < g.BY && (tbhi[2] - tb0[2]) < g.BX;
+    const bool load = ok && !outside;
+    s_geo[slot][6] = (ok ? 1 : 0) | (inside ? 2 : 0) | (outside ? 4 : 0) | (load ? 8 : 0);
+    s_geo[slot][7] = z0;
+    s_geo[slot][8] = y0;
+    s_geo[slot][9] = x0;
+    if (load) {
+      mbar_expect_tx(&bar[slot], static_cast<uint32_t>(g.bytes));
+      tma_load_3d(brick_base + slot * brick_stride, &src_map, &bar[slot], tb0[2], tb0[1], tb0[0]);
+    }
+  };
+
+  if (threadIdx.x == kBpConsumers) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    fence_mbar_init();
+    plan(blockIdx.x, 0);
+  }
+  __syncthreads();
+
+  // ---- loop-invariant per-thread constants
+  float mcol[3][3], half[3];
+  {
+    const int n[3] = {p.sz, p.sy, p.sx};
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) mcol[d][j] = g.mcol[3 * d + j];
+      half[d] = 0.5f * static_cast<float>(n[d] - 1);
+    }
+  }
+  constexpr uint32_t es = static_cast<uint32_t>(sizeof(T));
+  const uint32_t row_b = static_cast<uint32_t>(g.BX) * es;
+  const uint32_t plane_b = static_cast<uint32_t>(g.BY) * row_b;
+  const int64_t out_plane = static_cast<int64_t>(p.oy) * p.dpitch;
+  const int lane = threadIdx.x % kBrLanes, oth = threadIdx.x / kBrLanes;
+  uint32_t parity = 0;  // bit s: phase the consumers wait for on bar[s]
+
+  for (int it = 0, tile = blockIdx.x; tile < tiles_total; ++it, tile += gridDim.x) {
+    const int cur = it & 1;
+    // buffer cur^1 was last read in iteration it-1 (everyone passed its closing barrier)
+    if (threadIdx.x == kBpConsumers && tile + static_cast<int>(gridDim.x) < tiles_total)
+      plan(tile + gridDim.x, cur ^ 1);
+    const int flags = s_geo[cur][6];
+    if (!producer) {
+      const int z0 = s_geo[cur][7], y0 = s_geo[cur][8], x0 = s_geo[cur][9];
+      const int nz = min(kBrTZ, p.oz - z0);
+      if (flags & 4) {  // the whole tile maps outside the source: zeros, nothing was loaded
+        for (int i = threadIdx.x; i < nz * kTY * kTX; i += kBpConsumers) {
+          const int xx = i % kTX, yy = (i / kTX) % kTY, k = i / (kTX * kTY);
+          if (x0 + xx < p.ox && y0 + yy < p.oy)
+            st_global_cs(p.dst + (static_cast<int64_t>(z0 + k) * p.oy + y0 + yy) * p.dpitch + x0 + xx, 0.0f);
+        }
+      } else if (!(flags & 1)) {  // host bound too tight for this tile (never expected)
+#pragma unroll
+        for (int c = 0; c < kBrCols; ++c) {
+          const int y = y0 + oth + c * kBrRowStep, x = x0 + lane;
+          if (x < p.ox && y < p.oy)
+            for (int k = 0; k < nz; ++k)
+              p.dst[(static_cast<int64_t>(z0 + k) * p.oy + y) * p.dpitch + x] =
+                  affine_sample_generic<T, 1, BOUNDARY, SCRUB>(p, z0 + k, y, x);
+        }
+      } else {
+        int b0[3];
+        float c0l[3], mid[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          b0[d] = s_geo[cur][d];
+          c0l[d] = __int_as_float(s_geo[cur][3 + d]);
+          mid[d] = half[d] - static_cast<float>(b0[d]);
+        }
+        const bool tile_in = (flags & 2) != 0;
+        const uint32_t brick = brick_base + cur * brick_stride;
+        mbar_wait(&bar[cur], (parity >> cur) & 1u);
+#pragma unroll
+        for (int c = 0; c < kBrCols; ++c) {
+          const int yy = oth + c * kBrRowStep, xx = lane;
+          const int y = y0 + yy, x = x0 + xx;
+          if (x >= p.ox || y >= p.oy) continue;
+          float u0[3];
+#pragma unroll
+          for (int d = 0; d < 3; ++d)
+            u0[d] = __fmaf_rn(static_cast<float>(xx), mcol[d][2],
+                              __fmaf_rn(static_cast<float>(yy), mcol[d][1], c0l[d]));
+          float* __restrict__ out = p.dst + (static_cast<int64_t>(z0) * p.oy + y) * p.dpitch + x;
+          const BrickCol cc{brick, plane_b, row_b, out_plane, u0[0], u0[1], u0[2], mcol[0][0],
+                            mcol[1][0], mcol[2][0]};
+          uint32_t rest = tile_in
+                              ? brick_column_packed<T, false, false, kBrTZ, BOUNDARY>(cc, mid, half, out, nz)
+                              : brick_column_packed<T, true, false, kBrTZ, BOUNDARY>(cc, mid, half, out, nz);
+          // voxels near a decision edge, outside the source, or with non-finite taps: exact path
+          while (rest) {
+            const int k = __ffs(rest) - 1;
+            rest &= rest - 1;
+            const float kf = static_cast<float>(k);
+            const float dz = fabsf(__fmaf_rn(kf, mcol[0][0], u0[0]) - mid[0]);
+            const float dy = fabsf(__fmaf_rn(kf, mcol[1][0], u0[1]) - mid[1]);
+            const float dx = fabsf(__fmaf_rn(kf, mcol[2][0], u0[2]) - mid[2]);
+            const bool outside = dz > half[0] + 0.5f + kEdge || dy > half[1] + 0.5f + kEdge ||
+                                 dx > half[2] + 0.5f + kEdge;
+            const float v = outside ? 0.0f
+                                    : brick_sample_exact<T, 1, BOUNDARY, SCRUB>(
+                                          p, brick, b0[0], b0[1], b0[2], g.BZ, g.BY, g.BX, z0 + k, y, x);
+            st_global_cs(out + k * out_plane, v);
+          }
+        }
+      }
+    }
+    if (flags & 8) parity ^= 1u << cur;
+    __syncthreads();  // buffer cur and s_geo[cur] are free; s_geo[cur^1] is published
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
 template <typename T>
@@ -654,19 +839,25 @@ static bool brick_geometry_tz(const AffineParams& p, bool ly, int tz, int64_t ma
   return true;
 }
 
-template <typename T>
-static bool brick_geometry(const AffineParams& p, bool ly, bool finite_taps, BrickGeom* g,
-                           size_t* smem_bytes) {
-  if (reinterpret_cast<uintptr_t>(p.src) % 16 != 0) return false;
-  if ((static_cast<int64_t>(p.spitch) * sizeof(T)) % 16 != 0) return false;
+// float32 matrix columns for the fp32 increments + the |coordinate| bound over the whole output
+// (keeps the device-side int conversions defined)
+static bool brick_geometry_common(const AffineParams& p, BrickGeom* g) {
   for (int i = 0; i < 9; ++i) g->mcol[i] = static_cast<float>(p.m[4 * (i / 3) + (i % 3)]);
-  // |coordinate| bound over the whole output (keeps the device-side int conversions defined)
   for (int d = 0; d < 3; ++d) {
     const double reach = fabs(p.m[4 * d]) * (p.oz + fabs((double)p.cz)) +
                          fabs(p.m[4 * d + 1]) * (p.oy + fabs((double)p.cy)) +
                          fabs(p.m[4 * d + 2]) * (p.ox + fabs((double)p.cx)) + fabs(p.m[4 * d + 3]);
     if (!(reach < 1.0e9)) return false;
   }
+  return true;
+}
+
+template <typename T>
+static bool brick_geometry(const AffineParams& p, bool ly, bool finite_taps, BrickGeom* g,
+                           size_t* smem_bytes) {
+  if (reinterpret_cast<uintptr_t>(p.src) % 16 != 0) return false;
+  if ((static_cast<int64_t>(p.spitch) * sizeof(T)) % 16 != 0) return false;
+  if (!brick_geometry_common(p, g)) return false;
   // deep tiles when the output is deep enough to fill them and the brick still leaves 3 CTAs/SM
   // (3 x 74 KB + static shared memory < 227 KB); else 8-deep tiles, >= 3 CTAs/SM as well; larger
   // footprints use the gather path
@@ -719,8 +910,77 @@ static int launch_brick(const AffineParams& p, const BrickGeom& g, size_t smem_b
   return B2_OK;
 }
 
+template <typename T, int BOUNDARY>
+static int launch_brick_pers(const AffineParams& p, const BrickGeom& g, cudaStream_t stream) {
+  EncodeTiledFn encode = get_encode_tiled();
+  if (!encode) {
+    set_error("cuTensorMapEncodeTiled not available from the driver");
+    return B2_ERR_NO_DEVICE;
+  }
+  CUtensorMap map;
+  const cuuint64_t gdim[3] = {static_cast<cuuint64_t>(p.sx), static_cast<cuuint64_t>(p.sy),
+                              static_cast<cuuint64_t>(p.sz)};
+  const cuuint64_t gstride[2] = {static_cast<cuuint64_t>(p.spitch) * sizeof(T),
+                                 static_cast<cuuint64_t>(p.spitch) * p.sy * sizeof(T)};
+  const cuuint32_t box[3] = {static_cast<cuuint32_t>(g.BX), static_cast<cuuint32_t>(g.BY),
+                             static_cast<cuuint32_t>(g.BZ)};
+  const cuuint32_t estride[3] = {1, 1, 1};
+  const CUtensorMapDataType dt =
+      sizeof(T) == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  CUresult r = encode(&map, dt, 3, const_cast<void*>(p.src), gdim, gstride, box, estride,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (CUresult %d) for affine source (%d,%d,%d)", (int)r,
+              p.sz, p.sy, p.sx);
+    return B2_ERR_UNSUPPORTED;
+  }
+  const int tiles_z = (p.oz + kBrTZ - 1) / kBrTZ;
+  const int tiles_y = (p.oy + kBrOther - 1) / kBrOther;
+  const int tiles_x = (p.ox + kBrLanes - 1) / kBrLanes;
+  const int64_t tiles = static_cast<int64_t>(tiles_z) * tiles_y * tiles_x;
+  if (tiles > 2000000000LL) return B2_ERR_UNSUPPORTED;
+  int sms = 148;
+  sm_count(&sms);
+  const size_t smem = 2 * ((static_cast<size_t>(g.bytes) + 127) / 128 * 128) + 256;
+  auto kern = affine_brick_pers_kernel<T, BOUNDARY>;
+  B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                               cudaSharedmemCarveoutMaxShared));
+  const unsigned grid = static_cast<unsigned>(std::min<int64_t>(tiles, 2LL * sms));
+  kern<<<grid, kBpThreads, smem, stream>>>(map, p, g, tiles_z, tiles_x, static_cast<int>(tiles));
+  B2_CUDA(cudaGetLastError());
+  count_launch();
+  return B2_OK;
+}
+
+// B2_BRICK_PERSISTENT=0 selects the one-tile-per-CTA kernel for the cases the persistent one covers
+static bool brick_persistent_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("B2_BRICK_PERSISTENT");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
 template <typename T, bool LY>
 static int brick_typed_ly(const AffineParams& p, cudaStream_t stream, bool* eligible) {
+  if (!LY && p.order == 1 && ((p.scrub && sizeof(T) == 4) || sizeof(T) == 2) &&
+      brick_persistent_enabled()) {
+    // production case: persistent double-buffered kernel, two tight 8-deep bricks per CTA and two
+    // CTAs per SM (2 x 2 x 55 KB + static shared memory < 227 KB)
+    BrickGeom g{};
+    size_t smem = 0;
+    if (reinterpret_cast<uintptr_t>(p.src) % 16 == 0 &&
+        (static_cast<int64_t>(p.spitch) * sizeof(T)) % 16 == 0 &&
+        brick_geometry_common(p, &g) &&
+        brick_geometry_tz<T>(p, false, kBrTZ, 55 * 1024, &g, &smem)) {
+      *eligible = true;
+      return p.boundary == B2_BOUNDARY_CONSTANT
+                 ? launch_brick_pers<T, B2_BOUNDARY_CONSTANT>(p, g, stream)
+                 : launch_brick_pers<T, B2_BOUNDARY_ITK>(p, g, stream);
+    }
+  }
   BrickGeom g{};
   size_t smem = 0;
   const bool scrub = p.scrub && sizeof(T) == 4;

@@ -19,7 +19,7 @@ def launches(wl):
         a = agg.setdefault(name, [0, 0.0])
         a[0] += 1; a[1] += dur
     total = sum(v[1] for v in agg.values())
-    out = [f"# ncu launch list ({wl}; bench.py --steps 2 --warmup 3 --no-e2e --units 2; cold-cache serialised times: compare SHARES)",
+    out = [f"# ncu launch list ({wl}; bench.py --steps 2 --warmup 3 --no-e2e --no-extra --units 2; cold-cache serialised times: compare SHARES)",
            f"{'kernel':70s} {'launches':>8s} {'total_us':>10s} {'share':>7s}"]
     for name, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         out.append(f"{name:70s} {n:8d} {t:10.1f} {100*t/total:6.1f}%")
