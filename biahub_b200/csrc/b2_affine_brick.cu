@@ -158,7 +158,7 @@ __device__ __forceinline__ void brick_put(float* o, float v) {
 }
 
 struct BrickCol {
-  uint32_t brick, plane_b, row_b;
+  uint32_t brick, plane_b, row_b;  // `brick` = brick base MINUS kBrBiasOff(plane_b, row_b, es), see below
   int64_t out_plane;
   float u0z, u0y, u0x;  // brick-local coordinate of the column's first voxel
   float mz, my, mx;     // coordinate step per output plane (first column of the matrix)
@@ -300,7 +300,7 @@ __device__ __forceinline__ uint32_t brick_column_packed(const BrickCol& c, const
                                                         const float (&half)[3],
                                                         float* __restrict__ out, const int nz) {
   constexpr uint32_t es = static_cast<uint32_t>(sizeof(T));
-  const uint32_t abase = c.brick - 0x4B400000u * (c.plane_b + c.row_b + es);
+  const uint32_t abase = c.brick;  // the caller folded the magic-constant index biases in
   uint32_t rest = 0;
   float bad = 0.0f;  // turns NaN as soon as one voxel of the column is non-finite (v * 0 accumulates)
   float qa[4] = {0.0f, 0.0f, 0.0f, 0.0f};  // lo halves: taps (y0,x0) (y0,x1) (y1,x0) (y1,x1) of one plane
@@ -518,10 +518,11 @@ __global__ void __launch_bounds__(kBrThreads, 4)
 
     if (ORDER == 1 && (SCRUB || sizeof(T) == 2 || (nz == kBrTZ && g.TZ == kBrTZ))) {
       // ---- column fast path (order 1): see brick_column_packed / brick_column_linear
-      const BrickCol cc{brick, plane_b, row_b, out_plane, u0[0], u0[1], u0[2], mcol[0][0], mcol[1][0],
-                        mcol[2][0]};
+      BrickCol cc{brick, plane_b, row_b, out_plane, u0[0], u0[1], u0[2], mcol[0][0], mcol[1][0],
+                  mcol[2][0]};
       uint32_t rest;
       if (SCRUB || sizeof(T) == 2) {  // finite taps: packed arithmetic, any tile depth
+        cc.brick = brick - 0x4B400000u * (plane_b + row_b + es);  // index biases of the magic floors
         if (!LY && g.TZ == kBrTZMax) {
           rest = tile_in ? brick_column_packed<T, false, LY, kBrTZMax, BOUNDARY>(cc, mid, half, out, nz)
                          : brick_column_packed<T, true, LY, kBrTZMax, BOUNDARY>(cc, mid, half, out, nz);
@@ -649,7 +650,7 @@ constexpr int kBpConsumers = kBrThreads;        // 16 (y) x 32 (x) x kBrTZ tile,
 constexpr int kBpThreads = kBpConsumers + 32;   // + the producer warp
 
 template <typename T, int BOUNDARY>
-__global__ void __maxnreg__(112)  // 2 CTAs/SM: 2 x 288 threads x 112 registers <= 64 K
+__global__ void __maxnreg__(80)  // registers are per SM sub-partition (16 K): a 9-warp CTA puts 3 warps on one of them, two CTAs 6 -> 6 x 32 x 80 <= 16 K
     affine_brick_pers_kernel(const __grid_constant__ CUtensorMap src_map,
                              const __grid_constant__ AffineParams p,
                              const __grid_constant__ BrickGeom g, const int tiles_z,
@@ -725,6 +726,20 @@ __global__ void __maxnreg__(112)  // 2 CTAs/SM: 2 x 288 threads x 112 registers 
   const uint32_t plane_b = static_cast<uint32_t>(g.BY) * row_b;
   const int64_t out_plane = static_cast<int64_t>(p.oy) * p.dpitch;
   const int lane = threadIdx.x % kBrLanes, oth = threadIdx.x / kBrLanes;
+  // thread-invariant parts of the column start: coordinate offset of (yy = oth, xx = lane) from the
+  // tile origin, the step to the thread's second column (kBrRowStep rows further), the output
+  // offset inside a tile, and the index biases of the magic-constant floors
+  float t0[3], tstep[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    t0[d] = __fmaf_rn(static_cast<float>(lane), mcol[d][2], static_cast<float>(oth) * mcol[d][1]);
+    tstep[d] = static_cast<float>(kBrRowStep) * mcol[d][1];
+  }
+  const int64_t thr_off = static_cast<int64_t>(oth) * p.dpitch + lane;
+  const int64_t col_step = static_cast<int64_t>(kBrRowStep) * p.dpitch;
+  const uint32_t bias_off = 0x4B400000u * (plane_b + row_b + es);
+  const int oy = p.oy, ox = p.ox, oz = p.oz, dpitch = p.dpitch;
+  float* const dst = p.dst;
   uint32_t parity = 0;  // bit s: phase the consumers wait for on bar[s]
 
   for (int it = 0, tile = blockIdx.x; tile < tiles_total; ++it, tile += gridDim.x) {
@@ -735,7 +750,7 @@ __global__ void __maxnreg__(112)  // 2 CTAs/SM: 2 x 288 threads x 112 registers 
     const int flags = s_geo[cur][6];
     if (!producer) {
       const int z0 = s_geo[cur][7], y0 = s_geo[cur][8], x0 = s_geo[cur][9];
-      const int nz = min(kBrTZ, p.oz - z0);
+      const int nz = min(kBrTZ, oz - z0);
       if (flags & 4) {  // the whole tile maps outside the source: zeros, nothing was loaded
         for (int i = threadIdx.x; i < nz * kTY * kTX; i += kBpConsumers) {
           const int xx = i % kTX, yy = (i / kTX) % kTY, k = i / (kTX * kTY);
@@ -762,38 +777,40 @@ __global__ void __maxnreg__(112)  // 2 CTAs/SM: 2 x 288 threads x 112 registers 
         }
         const bool tile_in = (flags & 2) != 0;
         const uint32_t brick = brick_base + cur * brick_stride;
+        float* __restrict__ out = dst + (static_cast<int64_t>(z0) * oy + y0) * dpitch + x0 + thr_off;
+        float u0[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) u0[d] = c0l[d] + t0[d];
         mbar_wait(&bar[cur], (parity >> cur) & 1u);
 #pragma unroll
         for (int c = 0; c < kBrCols; ++c) {
-          const int yy = oth + c * kBrRowStep, xx = lane;
-          const int y = y0 + yy, x = x0 + xx;
-          if (x >= p.ox || y >= p.oy) continue;
-          float u0[3];
-#pragma unroll
-          for (int d = 0; d < 3; ++d)
-            u0[d] = __fmaf_rn(static_cast<float>(xx), mcol[d][2],
-                              __fmaf_rn(static_cast<float>(yy), mcol[d][1], c0l[d]));
-          float* __restrict__ out = p.dst + (static_cast<int64_t>(z0) * p.oy + y) * p.dpitch + x;
-          const BrickCol cc{brick, plane_b, row_b, out_plane, u0[0], u0[1], u0[2], mcol[0][0],
-                            mcol[1][0], mcol[2][0]};
-          uint32_t rest = tile_in
-                              ? brick_column_packed<T, false, false, kBrTZ, BOUNDARY>(cc, mid, half, out, nz)
-                              : brick_column_packed<T, true, false, kBrTZ, BOUNDARY>(cc, mid, half, out, nz);
-          // voxels near a decision edge, outside the source, or with non-finite taps: exact path
-          while (rest) {
-            const int k = __ffs(rest) - 1;
-            rest &= rest - 1;
-            const float kf = static_cast<float>(k);
-            const float dz = fabsf(__fmaf_rn(kf, mcol[0][0], u0[0]) - mid[0]);
-            const float dy = fabsf(__fmaf_rn(kf, mcol[1][0], u0[1]) - mid[1]);
-            const float dx = fabsf(__fmaf_rn(kf, mcol[2][0], u0[2]) - mid[2]);
-            const bool outside = dz > half[0] + 0.5f + kEdge || dy > half[1] + 0.5f + kEdge ||
-                                 dx > half[2] + 0.5f + kEdge;
-            const float v = outside ? 0.0f
-                                    : brick_sample_exact<T, 1, BOUNDARY, SCRUB>(
-                                          p, brick, b0[0], b0[1], b0[2], g.BZ, g.BY, g.BX, z0 + k, y, x);
-            st_global_cs(out + k * out_plane, v);
+          const int y = y0 + oth + c * kBrRowStep, x = x0 + lane;
+          if (x < ox && y < oy) {
+            const BrickCol cc{brick - bias_off, plane_b, row_b, out_plane, u0[0], u0[1], u0[2],
+                              mcol[0][0], mcol[1][0], mcol[2][0]};
+            uint32_t rest = tile_in
+                                ? brick_column_packed<T, false, false, kBrTZ, BOUNDARY>(cc, mid, half, out, nz)
+                                : brick_column_packed<T, true, false, kBrTZ, BOUNDARY>(cc, mid, half, out, nz);
+            // voxels near a decision edge, outside the source, or with non-finite taps: exact path
+            while (rest) {
+              const int k = __ffs(rest) - 1;
+              rest &= rest - 1;
+              const float kf = static_cast<float>(k);
+              const float dz = fabsf(__fmaf_rn(kf, mcol[0][0], u0[0]) - mid[0]);
+              const float dy = fabsf(__fmaf_rn(kf, mcol[1][0], u0[1]) - mid[1]);
+              const float dx = fabsf(__fmaf_rn(kf, mcol[2][0], u0[2]) - mid[2]);
+              const bool outside = dz > half[0] + 0.5f + kEdge || dy > half[1] + 0.5f + kEdge ||
+                                   dx > half[2] + 0.5f + kEdge;
+              const float v = outside ? 0.0f
+                                      : brick_sample_exact<T, 1, BOUNDARY, SCRUB>(
+                                            p, brick, b0[0], b0[1], b0[2], g.BZ, g.BY, g.BX, z0 + k, y, x);
+              st_global_cs(out + k * out_plane, v);
+            }
           }
+          // the thread's next column: kBrRowStep output rows further
+#pragma unroll
+          for (int d = 0; d < 3; ++d) u0[d] += tstep[d];
+          out += col_step;
         }
       }
     }
@@ -861,7 +878,11 @@ static bool brick_geometry(const AffineParams& p, bool ly, bool finite_taps, Bri
   // deep tiles when the output is deep enough to fill them and the brick still leaves 3 CTAs/SM
   // (3 x 74 KB + static shared memory < 227 KB); else 8-deep tiles, >= 3 CTAs/SM as well; larger
   // footprints use the gather path
-  if (!ly && finite_taps && p.order == 1 && p.oz > kBrTZ &&
+  static const bool deep_ok = [] {  // B2_BRICK_TZ=8 forces the shallow tiles (measurements)
+    const char* e = getenv("B2_BRICK_TZ");
+    return !(e && atoi(e) == kBrTZ);
+  }();
+  if (deep_ok && !ly && finite_taps && p.order == 1 && p.oz > kBrTZ &&
       brick_geometry_tz<T>(p, ly, kBrTZMax, 74 * 1024, g, smem_bytes))
     return true;
   return brick_geometry_tz<T>(p, ly, kBrTZ, 72 * 1024, g, smem_bytes);
@@ -965,8 +986,9 @@ static bool brick_persistent_enabled() {
 
 template <typename T, bool LY>
 static int brick_typed_ly(const AffineParams& p, cudaStream_t stream, bool* eligible) {
-  if (!LY && p.order == 1 && ((p.scrub && sizeof(T) == 4) || sizeof(T) == 2) &&
-      brick_persistent_enabled()) {
+  // (float32 sources; the uint16 instantiation of the persistent kernel spills under its register
+  // cap and stays on the one-tile-per-CTA kernel)
+  if (!LY && p.order == 1 && p.scrub && sizeof(T) == 4 && brick_persistent_enabled()) {
     // production case: persistent double-buffered kernel, two tight 8-deep bricks per CTA and two
     // CTAs per SM (2 x 2 x 55 KB + static shared memory < 227 KB)
     BrickGeom g{};
