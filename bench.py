@@ -915,7 +915,7 @@ def main():
 
     if w.get("plate"):
         # reader / GPU / writer stages keep up to four 1.5 GB results alive per rank
-        os.environ.setdefault("BIAHUB_B200_PINNED_POOL_MB", "12288")
+        os.environ.setdefault("BIAHUB_B200_PINNED_POOL_MB", "8192")
     if args.impl == "reference":
         res = run_reference(args, w, rank, world)
     else:

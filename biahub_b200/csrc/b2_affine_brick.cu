@@ -19,14 +19,11 @@
 
 namespace b2 {
 
-// Tile depth along z.  A deep tile amortises the z halo of its source brick: the kernel is bound by
-// the L2 -> shared-memory traffic of the bricks (8-deep tiles: 13 source planes per 8 output planes
-// and 3.3 source voxels staged per output voxel — 6.5 GB per C3-sized volume at the ~5.5 TB/s the
-// TMA boxes reach, which IS the 1.18 ms of the r1 kernel; 16-deep tiles with tight margins: 2.2).
-// 16 when the brick then still allows 3 CTAs/SM, else 8; the unrolled column routine is
-// instantiated for both depths.
-constexpr int kBrTZ = 8;      // depth of the legacy column routine (non-finite float32 taps)
-constexpr int kBrTZMax = 16;
+// Tile depth along z.  (16-deep tiles — less z halo per output voxel, 3 CTAs/SM — and a persistent
+// double-buffered variant with a producer warp were built in round 2, are bit-compatible, and
+// measure the same 1.2 ms on the C3-sized volume as 8-deep tiles: the kernel is bound by the
+// per-warp dependency chain, not by brick traffic, the TMA wait or the issue rate; git history.)
+constexpr int kBrTZ = 8;
 // In-plane tile: 16 (y) x 32 (x) with lanes along x; LY variant 32 (y) x 16 (x) with lanes along y
 // for matrices that map output y onto source x (90-degree in-plane rotations: with lanes along x
 // a warp's taps walk a brick column, 8-way bank conflicts) — its output goes through a padded
@@ -45,7 +42,6 @@ constexpr float kEdge = 2.0e-3f;
 constexpr float kMagic = 12582912.0f;  // 1.5 * 2^23: (v + kMagic) - kMagic rounds v to nearest
 
 struct BrickGeom {
-  int TZ;          // tile depth along z (kBrTZMax or kBrTZ)
   int BZ, BY, BX;  // brick extent (elements)
   int bytes;       // BZ*BY*BX*sizeof(T)
   // hull of a full tile relative to its origin voxel: sum of the negative / positive parts of
@@ -287,107 +283,127 @@ __device__ __forceinline__ void brick_quad_moved<uint16_t>(uint32_t a, uint32_t 
       : "r"(a), "r"(a_prev), "r"(row_b));
 }
 
-// One (y, x) column of a full-depth tile, order 1, FINITE taps (uint16, or float32 with the scrub:
-// a non-finite result sends the voxel to the exact path) — the packed-arithmetic form of
-// brick_column_linear.  The four in-plane taps of the two source planes sit in four register
-// PAIRS (lo half / hi half = the two planes); the upper plane of voxel k is the lower plane of
-// voxel k+1, so the halves swap roles from step to step (the loop is fully unrolled: the parity is
-// static) and only the upper plane is loaded — the lower one again only when the (y, x) cell moved.
-// Per voxel: 2 coordinate adds, 3 floors, 5 weight ops (y and x packed), 3 address, 1 compare,
-// 4 + 4 predicated LDS, 8 lerp instructions (3 FADD2 + 3 FFMA2 + 2 scalar), check + store.
-template <typename T, bool CHECK, bool LY, int TZ, int BOUNDARY>
-__device__ __forceinline__ uint32_t brick_column_packed(const BrickCol& c, const float (&mid)[3],
-                                                        const float (&half)[3],
-                                                        float* __restrict__ out, const int nz) {
+// NC (y, x) columns of a tile walked in LOCKSTEP, order 1, FINITE taps (uint16, or float32 with
+// the scrub: a non-finite result sends the column to the exact path) — the packed-arithmetic form
+// of brick_column_linear.
+//  * Per column the four in-plane taps of the two source planes sit in four register PAIRS (lo
+//    half / hi half = the two planes); the upper plane of voxel k is the lower plane of voxel k+1,
+//    so the halves swap roles from step to step (the loop is fully unrolled: the parity is static)
+//    and only the upper plane is loaded — the lower one again only when the (y, x) cell moved.
+//  * Per voxel: 2 coordinate adds, 3 floors, 5 weight ops (y and x packed), 3 address, 1 compare,
+//    4 + 4 predicated LDS, 8 lerp instructions (3 FADD2 + 3 FFMA2 + 2 scalar), check + store.
+//  * Why lockstep: one column is ONE dependency chain (coordinates -> address -> LDS -> lerps, and
+//    the tap hand-down serialises consecutive voxels); ncu showed every variant of this kernel
+//    (4, 3 or 2 CTAs/SM; 61, 53 or 46 instructions per voxel; TMA wait hidden or not) at the same
+//    1.2 ms with ~10 cycles between a warp's instructions.  Two independent chains in the same
+//    basic block give the scheduler something to issue in between.
+// Partial-depth tiles (nz < kBrTZ) compute every voxel (the brick always covers a full tile) and
+// only predicate the store.  `c[i].brick` has the magic-floor index biases folded in.
+template <typename T, bool CHECK, bool LY, int BOUNDARY, int NC>
+__device__ __forceinline__ void brick_columns_packed(const BrickCol (&c)[NC], const float (&mid)[3],
+                                                     const float (&half)[3],
+                                                     float* const (&out)[NC], const int nz,
+                                                     uint32_t (&rest)[NC]) {
   constexpr uint32_t es = static_cast<uint32_t>(sizeof(T));
-  const uint32_t abase = c.brick;  // the caller folded the magic-constant index biases in
-  uint32_t rest = 0;
-  float bad = 0.0f;  // turns NaN as soon as one voxel of the column is non-finite (v * 0 accumulates)
-  float qa[4] = {0.0f, 0.0f, 0.0f, 0.0f};  // lo halves: taps (y0,x0) (y0,x1) (y1,x0) (y1,x1) of one plane
-  float qb[4] = {0.0f, 0.0f, 0.0f, 0.0f};  // hi halves: the same taps of the other plane
-  uint32_t a_up = 0xffffffffu;
-  float uz = c.u0z;
-  f32x2 uyx = pk2(c.u0y, c.u0x);
-  const f32x2 myx = pk2(c.my, c.mx);
-  const f32x2 magic2 = pk2(kMagic, kMagic);
-  // the output pointer walks one plane per voxel as a BYTE pointer (one 64-bit add, no index scaling)
-  char* __restrict__ o = reinterpret_cast<char*>(out);
-  const int64_t plane_bytes = c.out_plane * 4;
-  // partial-depth tiles (nz < TZ) compute every voxel of the column (the brick always covers a
-  // full tile) and only predicate the store
+  float bad[NC];      // turns NaN as soon as one voxel of the column is non-finite (v * 0 accumulates)
+  float qa[NC][4];    // lo halves: taps (y0,x0) (y0,x1) (y1,x0) (y1,x1) of one plane
+  float qb[NC][4];    // hi halves: the same taps of the other plane
+  uint32_t a_up[NC];
+  float uz[NC];
+  f32x2 uyx[NC], myx[NC];
+  char* o[NC];        // byte pointers: one 64-bit add per plane, no index scaling
 #pragma unroll
-  for (int k = 0; k < TZ; ++k) {
-    bool interior = true;
-    float cz = uz;       // the coordinate this voxel samples at (clamped in the ITK band)
-    f32x2 cyx = uyx;
-    if (CHECK) {
-      float uy, ux;
-      upk2(uyx, uy, ux);
-      if (BOUNDARY == B2_BOUNDARY_ITK) {
-        // ITK: inside iff -0.5 <= c < n - 0.5, and inside the half-voxel band the interpolator
-        // clamps to the edge voxel (base clamped, neighbour dropped) = trilinear at the CLAMPED
-        // coordinate, continuous across c = 0 and c = n-1: only the +-0.5 edges are decisions
-        interior = fabsf(uz - mid[0]) <= half[0] + 0.5f - kEdge &&
-                   fabsf(uy - mid[1]) <= half[1] + 0.5f - kEdge &&
-                   fabsf(ux - mid[2]) <= half[2] + 0.5f - kEdge;
-        cz = fminf(fmaxf(uz, mid[0] - half[0]), mid[0] + half[0]);
-        cyx = pk2(fminf(fmaxf(uy, mid[1] - half[1]), mid[1] + half[1]),
-                  fminf(fmaxf(ux, mid[2] - half[2]), mid[2] + half[2]));
-      } else {
-        interior = fabsf(uz - mid[0]) <= half[0] - kEdge && fabsf(uy - mid[1]) <= half[1] - kEdge &&
-                   fabsf(ux - mid[2]) <= half[2] - kEdge;
-      }
-    }
-    if (interior) {
-      const float tz = __fadd_rd(cz, kMagic);
-      const f32x2 tyx = add2_rd(cyx, magic2);
-      const float wz = cz - (tz - kMagic);
-      const f32x2 wyx = sub2(cyx, sub2(tyx, magic2));
-      float ty, tx, wy, wx;
-      upk2(tyx, ty, tx);
-      upk2(wyx, wy, wx);
-      const uint32_t a00 = static_cast<uint32_t>(__float_as_int(tz)) * c.plane_b +
-                           (static_cast<uint32_t>(__float_as_int(ty)) * c.row_b +
-                            (static_cast<uint32_t>(__float_as_int(tx)) * es + abase));
-      const uint32_t a10 = a00 + c.plane_b;
-      float (&lo)[4] = (k & 1) ? qb : qa;  // lower source plane of this voxel
-      float (&up)[4] = (k & 1) ? qa : qb;  // upper source plane: loaded now, lower plane next step
-      brick_quad_moved<T>(a00, a_up, c.row_b, lo[0], lo[1], lo[2], lo[3]);
-      up[0] = brick_elem<T>(a10);
-      up[1] = brick_elem<T>(a10 + es);
-      up[2] = brick_elem<T>(a10 + c.row_b);
-      up[3] = brick_elem<T>(a10 + c.row_b + es);
-      a_up = a10;
-      const f32x2 q00 = pk2(qa[0], qb[0]), q01 = pk2(qa[1], qb[1]);
-      const f32x2 q10 = pk2(qa[2], qb[2]), q11 = pk2(qa[3], qb[3]);
-      const f32x2 wx2 = pk2(wx, wx), wy2 = pk2(wy, wy);
-      const f32x2 x0 = fma2(wx2, sub2(q01, q00), q00);  // x lerp on row y0 of both planes
-      const f32x2 x1 = fma2(wx2, sub2(q11, q10), q10);  // ... on row y1
-      const f32x2 yy = fma2(wy2, sub2(x1, x0), x0);     // in-plane bilinear value of both planes
-      float pa, pb;
-      upk2(yy, pa, pb);
-      const float vlo = (k & 1) ? pb : pa, vup = (k & 1) ? pa : pb;
-      const float v = __fmaf_rn(wz, vup - vlo, vlo);
-      // a NaN/inf tap makes v non-finite; the voxel is stored anyway and the whole column is
-      // redone on the exact path (which applies the scrub per tap) after the loop
-      if (sizeof(T) == 4) bad = __fmaf_rn(v, 0.0f, bad);
-      if (k < nz) brick_put<LY>(reinterpret_cast<float*>(o), v);
-    } else {
-      if (k < nz) rest |= 1u << k;
-      a_up = 0xffffffffu;
-    }
-    uz += c.mz;
-    uyx = add2(uyx, myx);
-    o += plane_bytes;
+  for (int i = 0; i < NC; ++i) {
+    bad[i] = 0.0f;
+    rest[i] = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) qa[i][j] = qb[i][j] = 0.0f;
+    a_up[i] = 0xffffffffu;
+    uz[i] = c[i].u0z;
+    uyx[i] = pk2(c[i].u0y, c[i].u0x);
+    myx[i] = pk2(c[i].my, c[i].mx);
+    o[i] = reinterpret_cast<char*>(out[i]);
   }
-  return (bad != bad) ? ((1u << nz) - 1u) : rest;
+  const f32x2 magic2 = pk2(kMagic, kMagic);
+  const int64_t plane_bytes = c[0].out_plane * 4;
+#pragma unroll
+  for (int k = 0; k < kBrTZ; ++k) {
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+      bool interior = true;
+      float cz = uz[i];       // the coordinate this voxel samples at (clamped in the ITK band)
+      f32x2 cyx = uyx[i];
+      if (CHECK) {
+        float uy, ux;
+        upk2(uyx[i], uy, ux);
+        if (BOUNDARY == B2_BOUNDARY_ITK) {
+          // ITK: inside iff -0.5 <= c < n - 0.5, and inside the half-voxel band the interpolator
+          // clamps to the edge voxel (base clamped, neighbour dropped) = trilinear at the CLAMPED
+          // coordinate, continuous across c = 0 and c = n-1: only the +-0.5 edges are decisions
+          interior = fabsf(uz[i] - mid[0]) <= half[0] + 0.5f - kEdge &&
+                     fabsf(uy - mid[1]) <= half[1] + 0.5f - kEdge &&
+                     fabsf(ux - mid[2]) <= half[2] + 0.5f - kEdge;
+          cz = fminf(fmaxf(uz[i], mid[0] - half[0]), mid[0] + half[0]);
+          cyx = pk2(fminf(fmaxf(uy, mid[1] - half[1]), mid[1] + half[1]),
+                    fminf(fmaxf(ux, mid[2] - half[2]), mid[2] + half[2]));
+        } else {
+          interior = fabsf(uz[i] - mid[0]) <= half[0] - kEdge && fabsf(uy - mid[1]) <= half[1] - kEdge &&
+                     fabsf(ux - mid[2]) <= half[2] - kEdge;
+        }
+      }
+      if (interior) {
+        const float tz = __fadd_rd(cz, kMagic);
+        const f32x2 tyx = add2_rd(cyx, magic2);
+        const float wz = cz - (tz - kMagic);
+        const f32x2 wyx = sub2(cyx, sub2(tyx, magic2));
+        float ty, tx, wy, wx;
+        upk2(tyx, ty, tx);
+        upk2(wyx, wy, wx);
+        const uint32_t a00 = static_cast<uint32_t>(__float_as_int(tz)) * c[i].plane_b +
+                             (static_cast<uint32_t>(__float_as_int(ty)) * c[i].row_b +
+                              (static_cast<uint32_t>(__float_as_int(tx)) * es + c[i].brick));
+        const uint32_t a10 = a00 + c[i].plane_b;
+        float (&lo)[4] = (k & 1) ? qb[i] : qa[i];  // lower source plane of this voxel
+        float (&up)[4] = (k & 1) ? qa[i] : qb[i];  // upper plane: loaded now, lower plane next step
+        brick_quad_moved<T>(a00, a_up[i], c[i].row_b, lo[0], lo[1], lo[2], lo[3]);
+        up[0] = brick_elem<T>(a10);
+        up[1] = brick_elem<T>(a10 + es);
+        up[2] = brick_elem<T>(a10 + c[i].row_b);
+        up[3] = brick_elem<T>(a10 + c[i].row_b + es);
+        a_up[i] = a10;
+        const f32x2 q00 = pk2(qa[i][0], qb[i][0]), q01 = pk2(qa[i][1], qb[i][1]);
+        const f32x2 q10 = pk2(qa[i][2], qb[i][2]), q11 = pk2(qa[i][3], qb[i][3]);
+        const f32x2 wx2 = pk2(wx, wx), wy2 = pk2(wy, wy);
+        const f32x2 x0 = fma2(wx2, sub2(q01, q00), q00);  // x lerp on row y0 of both planes
+        const f32x2 x1 = fma2(wx2, sub2(q11, q10), q10);  // ... on row y1
+        const f32x2 yy = fma2(wy2, sub2(x1, x0), x0);     // in-plane bilinear value of both planes
+        float pa, pb;
+        upk2(yy, pa, pb);
+        const float vlo = (k & 1) ? pb : pa, vup = (k & 1) ? pa : pb;
+        const float v = __fmaf_rn(wz, vup - vlo, vlo);
+        // a NaN/inf tap makes v non-finite; the voxel is stored anyway and the whole column is
+        // redone on the exact path (which applies the scrub per tap) after the loop
+        if (sizeof(T) == 4) bad[i] = __fmaf_rn(v, 0.0f, bad[i]);
+        if (k < nz) brick_put<LY>(reinterpret_cast<float*>(o[i]), v);
+      } else {
+        if (k < nz) rest[i] |= 1u << k;
+        a_up[i] = 0xffffffffu;
+      }
+      uz[i] += c[i].mz;
+      uyx[i] = add2(uyx[i], myx[i]);
+      o[i] += plane_bytes;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NC; ++i)
+    if (bad[i] != bad[i]) rest[i] = (1u << nz) - 1u;
 }
 
 template <typename T, int ORDER, int BOUNDARY, bool SCRUB, bool LY>
 __global__ void __launch_bounds__(kBrThreads, 4)
     affine_brick_kernel(const __grid_constant__ CUtensorMap src_map,
                         const __grid_constant__ AffineParams p,
-                        const __grid_constant__ BrickGeom g, const int tiles_z, const int tiles_x) {
+                        const __grid_constant__ BrickGeom g) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t bar;
   constexpr int kVec = 16 / static_cast<int>(sizeof(T));
@@ -398,11 +414,11 @@ __global__ void __launch_bounds__(kBrThreads, 4)
   float* stage_out = reinterpret_cast<float*>(smem_al + ((g.bytes + 127) / 128) * 128);
 
   // z-fastest rasterisation: consecutive CTAs share z-halo planes
-  const int tz_i = blockIdx.x % tiles_z;
-  const int tx_i = (blockIdx.x / tiles_z) % tiles_x;
-  const int ty_i = blockIdx.x / (tiles_z * tiles_x);
-  const int z0 = tz_i * g.TZ, y0 = ty_i * kBrTY, x0 = tx_i * kBrTX;
-  const int nz = min(g.TZ, p.oz - z0);
+  // 3-D grid (z tiles, x tiles, y tiles): x is the fastest launch dimension, so the rasterisation
+  // is z-fastest without the two runtime integer divisions a flat tile index costs every warp
+  const int tz_i = blockIdx.x, tx_i = blockIdx.y, ty_i = blockIdx.z;
+  const int z0 = tz_i * kBrTZ, y0 = ty_i * kBrTY, x0 = tx_i * kBrTX;
+  const int nz = min(kBrTZ, p.oz - z0);
 
   // ---- brick origin: exact float64 coordinate of the tile origin + the host-computed hull of a
   //      full tile (the kBrGuard slack absorbs the rounding of the hull sums and the fp32 error of
@@ -498,58 +514,104 @@ __global__ void __launch_bounds__(kBrThreads, 4)
   // staged tile in shared memory (LY)
   const int64_t out_plane = LY ? static_cast<int64_t>(kBrTY * kBrOutPitch)
                                : static_cast<int64_t>(p.oy) * p.dpitch;
-#pragma unroll
-  for (int c = 0; c < kBrCols; ++c) {
-    const int o2 = oth + c * kBrRowStep;
-    const int yy = LY ? lane : o2, xx = LY ? o2 : lane;
-    const int y = y0 + yy, x = x0 + xx;
-    if (x >= p.ox || y >= p.oy) continue;
-    // column start (fp32, brick-local): tile origin + yy*col1 + xx*col2
-    float u0[3];
+  // the thread's kBrCols columns: (yy, xx), validity, brick-local start coordinate, output pointer
+  bool col_ok[kBrCols];
+  int col_y[kBrCols], col_x[kBrCols];
+  float u0s[kBrCols][3];
+  float* outs[kBrCols];
+  {
+    // column 0 from the tile origin; the following ones step kBrRowStep positions along the
+    // non-lane axis (3 FADD + one pointer add each instead of 6 FFMA + a 64-bit index product)
+    const int yy = LY ? lane : oth, xx = LY ? oth : lane;
+    col_y[0] = y0 + yy;
+    col_x[0] = x0 + xx;
 #pragma unroll
     for (int d = 0; d < 3; ++d)
-      u0[d] = __fmaf_rn(static_cast<float>(xx), mcol[d][2],
-                        __fmaf_rn(static_cast<float>(yy), mcol[d][1], c0l[d]));
-    float* __restrict__ out =
-        LY ? stage_out + yy * kBrOutPitch + xx
-           : p.dst + (static_cast<int64_t>(z0) * p.oy + y) * p.dpitch + x;
+      u0s[0][d] = __fmaf_rn(static_cast<float>(xx), mcol[d][2],
+                            __fmaf_rn(static_cast<float>(yy), mcol[d][1], c0l[d]));
+    outs[0] = LY ? stage_out + yy * kBrOutPitch + xx
+                 : p.dst + (static_cast<int64_t>(z0) * p.oy + col_y[0]) * p.dpitch + col_x[0];
+    const int64_t ostep = LY ? static_cast<int64_t>(kBrRowStep)
+                             : static_cast<int64_t>(kBrRowStep) * p.dpitch;
+#pragma unroll
+    for (int c = 1; c < kBrCols; ++c) {
+      col_y[c] = col_y[c - 1] + (LY ? 0 : kBrRowStep);
+      col_x[c] = col_x[c - 1] + (LY ? kBrRowStep : 0);
+#pragma unroll
+      for (int d = 0; d < 3; ++d)
+        u0s[c][d] = __fmaf_rn(static_cast<float>(kBrRowStep), mcol[d][LY ? 2 : 1], u0s[c - 1][d]);
+      outs[c] = outs[c - 1] + ostep;
+    }
+#pragma unroll
+    for (int c = 0; c < kBrCols; ++c) col_ok[c] = col_x[c] < p.ox && col_y[c] < p.oy;
+  }
+  // voxels the fast path left: near a decision edge, outside the source, or non-finite taps
+  auto finish_exact = [&](int c, uint32_t rest) {
+    while (rest) {
+      const int k = __ffs(rest) - 1;
+      rest &= rest - 1;
+      const float kf = static_cast<float>(k);
+      const float dz = fabsf(__fmaf_rn(kf, mcol[0][0], u0s[c][0]) - mid[0]);
+      const float dy = fabsf(__fmaf_rn(kf, mcol[1][0], u0s[c][1]) - mid[1]);
+      const float dx = fabsf(__fmaf_rn(kf, mcol[2][0], u0s[c][2]) - mid[2]);
+      const bool outside = dz > half[0] + 0.5f + kEdge || dy > half[1] + 0.5f + kEdge ||
+                           dx > half[2] + 0.5f + kEdge;
+      const float v = outside ? 0.0f
+                              : brick_sample_exact<T, ORDER, BOUNDARY, SCRUB>(
+                                    p, brick, b0[0], b0[1], b0[2], g.BZ, g.BY, g.BX, z0 + k, col_y[c],
+                                    col_x[c]);
+      brick_put<LY>(outs[c] + k * out_plane, v);
+    }
+  };
+  constexpr bool kPacked = ORDER == 1 && (SCRUB || sizeof(T) == 2);  // finite taps
+  if (kPacked) {
+    const uint32_t biased = brick - 0x4B400000u * (plane_b + row_b + es);  // magic-floor index biases
+    bool all_ok = true;
+#pragma unroll
+    for (int c = 0; c < kBrCols; ++c) all_ok = all_ok && col_ok[c];
+    if (all_ok) {
+      // ---- both columns in lockstep (every tile but the ragged ones at the volume's y / x end)
+      BrickCol cc[kBrCols];
+#pragma unroll
+      for (int c = 0; c < kBrCols; ++c)
+        cc[c] = BrickCol{biased, plane_b, row_b, out_plane, u0s[c][0], u0s[c][1], u0s[c][2],
+                         mcol[0][0], mcol[1][0], mcol[2][0]};
+      uint32_t rest[kBrCols];
+      if (tile_in) {
+        brick_columns_packed<T, false, LY, BOUNDARY, kBrCols>(cc, mid, half, outs, nz, rest);
+      } else {
+        brick_columns_packed<T, true, LY, BOUNDARY, kBrCols>(cc, mid, half, outs, nz, rest);
+      }
+#pragma unroll
+      for (int c = 0; c < kBrCols; ++c) finish_exact(c, rest[c]);
+    } else {
+#pragma unroll
+      for (int c = 0; c < kBrCols; ++c) {
+        if (!col_ok[c]) continue;
+        const BrickCol cc[1] = {BrickCol{biased, plane_b, row_b, out_plane, u0s[c][0], u0s[c][1],
+                                         u0s[c][2], mcol[0][0], mcol[1][0], mcol[2][0]}};
+        float* const o1[1] = {outs[c]};
+        uint32_t rest[1];
+        brick_columns_packed<T, true, LY, BOUNDARY, 1>(cc, mid, half, o1, nz, rest);
+        finish_exact(c, rest[0]);
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < kBrCols; ++c) {
+    if (kPacked || !col_ok[c]) continue;
+    const int y = col_y[c], x = col_x[c];
+    const float (&u0)[3] = u0s[c];
+    float* __restrict__ out = outs[c];
     uint32_t todo = 0;  // bit k: voxel k is not strictly interior -> handled after the hot loop
     float* __restrict__ o = out;
-
-    if (ORDER == 1 && (SCRUB || sizeof(T) == 2 || (nz == kBrTZ && g.TZ == kBrTZ))) {
-      // ---- column fast path (order 1): see brick_column_packed / brick_column_linear
-      BrickCol cc{brick, plane_b, row_b, out_plane, u0[0], u0[1], u0[2], mcol[0][0], mcol[1][0],
-                  mcol[2][0]};
-      uint32_t rest;
-      if (SCRUB || sizeof(T) == 2) {  // finite taps: packed arithmetic, any tile depth
-        cc.brick = brick - 0x4B400000u * (plane_b + row_b + es);  // index biases of the magic floors
-        if (!LY && g.TZ == kBrTZMax) {
-          rest = tile_in ? brick_column_packed<T, false, LY, kBrTZMax, BOUNDARY>(cc, mid, half, out, nz)
-                         : brick_column_packed<T, true, LY, kBrTZMax, BOUNDARY>(cc, mid, half, out, nz);
-        } else {
-          rest = tile_in ? brick_column_packed<T, false, LY, kBrTZ, BOUNDARY>(cc, mid, half, out, nz)
-                         : brick_column_packed<T, true, LY, kBrTZ, BOUNDARY>(cc, mid, half, out, nz);
-        }
-      } else if (tile_in) {
-        rest = brick_column_linear<T, SCRUB, false, LY>(cc, mid, half, out);
-      } else {
-        rest = brick_column_linear<T, SCRUB, true, LY>(cc, mid, half, out);
-      }
-      // voxels near a decision edge, outside the source, or with non-finite taps: exact path
-      while (rest) {
-        const int k = __ffs(rest) - 1;
-        rest &= rest - 1;
-        const float kf = static_cast<float>(k);
-        const float dz = fabsf(__fmaf_rn(kf, mcol[0][0], u0[0]) - mid[0]);
-        const float dy = fabsf(__fmaf_rn(kf, mcol[1][0], u0[1]) - mid[1]);
-        const float dx = fabsf(__fmaf_rn(kf, mcol[2][0], u0[2]) - mid[2]);
-        const bool outside = dz > half[0] + 0.5f + kEdge || dy > half[1] + 0.5f + kEdge ||
-                             dx > half[2] + 0.5f + kEdge;
-        const float v = outside ? 0.0f
-                                : brick_sample_exact<T, ORDER, BOUNDARY, SCRUB>(
-                                      p, brick, b0[0], b0[1], b0[2], g.BZ, g.BY, g.BX, z0 + k, y, x);
-        brick_put<LY>(out + k * out_plane, v);
-      }
+    if (ORDER == 1 && nz == kBrTZ) {
+      // ---- float32 taps that may be non-finite (scrub off): brick_column_linear
+      const BrickCol cc{brick, plane_b, row_b, out_plane, u0[0], u0[1], u0[2], mcol[0][0], mcol[1][0],
+                        mcol[2][0]};
+      const uint32_t rest = tile_in ? brick_column_linear<T, SCRUB, false, LY>(cc, mid, half, out)
+                                    : brick_column_linear<T, SCRUB, true, LY>(cc, mid, half, out);
+      finish_exact(c, rest);
       continue;
     }
 #pragma unroll 2
@@ -636,190 +698,6 @@ __global__ void __launch_bounds__(kBrThreads, 4)
 }
 
 // ---------------------------------------------------------------------------------------------
-// Persistent, double-buffered form of the kernel above for the production case (order 1, finite
-// taps, lanes along x).  The one-tile-per-CTA kernel spends 20-27 % of its resident warp time in
-// the mbarrier wait at the start of each tile (ncu source page: the `try_wait` branch) and ~10 %
-// of its instructions in per-CTA set-up.  Here a CTA (8 consumer warps + 1 producer warp, 2 CTAs
-// per SM) walks a strided sequence of tiles with TWO brick buffers: while the consumers work on
-// tile i from one buffer, the producer evaluates the geometry of tile i+1 (float64, tile decode
-// included) and has its TMA box load in flight into the other one; one CTA barrier per tile hands
-// the buffers over.  Loop-invariant set-up (matrix columns, strides, lane coordinates) is done
-// once per CTA.
-// ---------------------------------------------------------------------------------------------
-constexpr int kBpConsumers = kBrThreads;        // 16 (y) x 32 (x) x kBrTZ tile, two columns per thread
-constexpr int kBpThreads = kBpConsumers + 32;   // + the producer warp
-
-template <typename T, int BOUNDARY>
-__global__ void __maxnreg__(80)  // registers are per SM sub-partition (16 K): a 9-warp CTA puts 3 warps on one of them, two CTAs 6 -> 6 x 32 x 80 <= 16 K
-    affine_brick_pers_kernel(const __grid_constant__ CUtensorMap src_map,
-                             const __grid_constant__ AffineParams p,
-                             const __grid_constant__ BrickGeom g, const int tiles_z,
-                             const int tiles_x, const int tiles_total) {
-  constexpr bool SCRUB = sizeof(T) == 4;  // float32 taps are scrubbed on the exact path
-  constexpr int kVec = 16 / static_cast<int>(sizeof(T));
-  constexpr int kTY = kBrOther, kTX = kBrLanes;
-  extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t bar[2];
-  // per buffer: b0[3], bits(c0l[3]), flags (1 brick ok, 2 interior, 4 outside, 8 load issued), z0, y0, x0
-  __shared__ int s_geo[2][12];
-  uint8_t* smem_al = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
-  const uint32_t brick_stride = static_cast<uint32_t>((g.bytes + 127) / 128) * 128u;
-  const uint32_t brick_base = smem_u32(smem_al);
-  const bool producer = threadIdx.x >= kBpConsumers;
-
-  // geometry of `tile` into buffer `slot` + its TMA load (one thread of the producer warp)
-  auto plan = [&](int tile, int slot) {
-    const int tz_i = tile % tiles_z;
-    const int tx_i = (tile / tiles_z) % tiles_x;
-    const int ty_i = tile / (tiles_z * tiles_x);
-    const int z0 = tz_i * kBrTZ, y0 = ty_i * kTY, x0 = tx_i * kTX;
-    int tb0[3], tbhi[3];
-    const double zf = static_cast<double>(z0 + p.cz), yf = static_cast<double>(y0 + p.cy),
-                 xf = static_cast<double>(x0 + p.cx);
-    const int n[3] = {p.sz, p.sy, p.sx};
-    bool inside = true, outside = false;
-#pragma unroll
-    for (int d = 0; d < 3; ++d) {
-      const double c = coord_full(p.m + 4 * d, zf, yf, xf);
-      tb0[d] = __double2int_rd(c + (g.neg[d] - kBrGuard));
-      outside = outside || tb0[d] >= n[d] + 1 || __double2int_rd(c + (g.pos[d] + kBrGuard)) <= -2;
-      inside = inside && tb0[d] >= 1;
-      if (d == 2) tb0[d] &= ~(kVec - 1);  // innermost TMA coordinate must be 16-byte aligned
-      tbhi[d] = __double2int_rd(c + (g.pos[d] + kBrGuard)) + 1;  // index of the last tap
-      inside = inside && tbhi[d] <= n[d] - 2;
-      s_geo[slot][d] = tb0[d];
-      s_geo[slot][3 + d] = __float_as_int(static_cast<float>(c - static_cast<double>(tb0[d])));
-    }
-    const bool ok = (tbhi[0] - tb0[0]) < g.BZ && (tbhi[1] - tb0[1]) < g.BY && (tbhi[2] - tb0[2]) < g.BX;
-    const bool load = ok && !outside;
-    s_geo[slot][6] = (ok ? 1 : 0) | (inside ? 2 : 0) | (outside ? 4 : 0) | (load ? 8 : 0);
-    s_geo[slot][7] = z0;
-    s_geo[slot][8] = y0;
-    s_geo[slot][9] = x0;
-    if (load) {
-      mbar_expect_tx(&bar[slot], static_cast<uint32_t>(g.bytes));
-      tma_load_3d(brick_base + slot * brick_stride, &src_map, &bar[slot], tb0[2], tb0[1], tb0[0]);
-    }
-  };
-
-  if (threadIdx.x == kBpConsumers) {
-    mbar_init(&bar[0], 1);
-    mbar_init(&bar[1], 1);
-    fence_mbar_init();
-    plan(blockIdx.x, 0);
-  }
-  __syncthreads();
-
-  // ---- loop-invariant per-thread constants
-  float mcol[3][3], half[3];
-  {
-    const int n[3] = {p.sz, p.sy, p.sx};
-#pragma unroll
-    for (int d = 0; d < 3; ++d) {
-#pragma unroll
-      for (int j = 0; j < 3; ++j) mcol[d][j] = g.mcol[3 * d + j];
-      half[d] = 0.5f * static_cast<float>(n[d] - 1);
-    }
-  }
-  constexpr uint32_t es = static_cast<uint32_t>(sizeof(T));
-  const uint32_t row_b = static_cast<uint32_t>(g.BX) * es;
-  const uint32_t plane_b = static_cast<uint32_t>(g.BY) * row_b;
-  const int64_t out_plane = static_cast<int64_t>(p.oy) * p.dpitch;
-  const int lane = threadIdx.x % kBrLanes, oth = threadIdx.x / kBrLanes;
-  // thread-invariant parts of the column start: coordinate offset of (yy = oth, xx = lane) from the
-  // tile origin, the step to the thread's second column (kBrRowStep rows further), the output
-  // offset inside a tile, and the index biases of the magic-constant floors
-  float t0[3], tstep[3];
-#pragma unroll
-  for (int d = 0; d < 3; ++d) {
-    t0[d] = __fmaf_rn(static_cast<float>(lane), mcol[d][2], static_cast<float>(oth) * mcol[d][1]);
-    tstep[d] = static_cast<float>(kBrRowStep) * mcol[d][1];
-  }
-  const int64_t thr_off = static_cast<int64_t>(oth) * p.dpitch + lane;
-  const int64_t col_step = static_cast<int64_t>(kBrRowStep) * p.dpitch;
-  const uint32_t bias_off = 0x4B400000u * (plane_b + row_b + es);
-  const int oy = p.oy, ox = p.ox, oz = p.oz, dpitch = p.dpitch;
-  float* const dst = p.dst;
-  uint32_t parity = 0;  // bit s: phase the consumers wait for on bar[s]
-
-  for (int it = 0, tile = blockIdx.x; tile < tiles_total; ++it, tile += gridDim.x) {
-    const int cur = it & 1;
-    // buffer cur^1 was last read in iteration it-1 (everyone passed its closing barrier)
-    if (threadIdx.x == kBpConsumers && tile + static_cast<int>(gridDim.x) < tiles_total)
-      plan(tile + gridDim.x, cur ^ 1);
-    const int flags = s_geo[cur][6];
-    if (!producer) {
-      const int z0 = s_geo[cur][7], y0 = s_geo[cur][8], x0 = s_geo[cur][9];
-      const int nz = min(kBrTZ, oz - z0);
-      if (flags & 4) {  // the whole tile maps outside the source: zeros, nothing was loaded
-        for (int i = threadIdx.x; i < nz * kTY * kTX; i += kBpConsumers) {
-          const int xx = i % kTX, yy = (i / kTX) % kTY, k = i / (kTX * kTY);
-          if (x0 + xx < p.ox && y0 + yy < p.oy)
-            st_global_cs(p.dst + (static_cast<int64_t>(z0 + k) * p.oy + y0 + yy) * p.dpitch + x0 + xx, 0.0f);
-        }
-      } else if (!(flags & 1)) {  // host bound too tight for this tile (never expected)
-#pragma unroll
-        for (int c = 0; c < kBrCols; ++c) {
-          const int y = y0 + oth + c * kBrRowStep, x = x0 + lane;
-          if (x < p.ox && y < p.oy)
-            for (int k = 0; k < nz; ++k)
-              p.dst[(static_cast<int64_t>(z0 + k) * p.oy + y) * p.dpitch + x] =
-                  affine_sample_generic<T, 1, BOUNDARY, SCRUB>(p, z0 + k, y, x);
-        }
-      } else {
-        int b0[3];
-        float c0l[3], mid[3];
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-          b0[d] = s_geo[cur][d];
-          c0l[d] = __int_as_float(s_geo[cur][3 + d]);
-          mid[d] = half[d] - static_cast<float>(b0[d]);
-        }
-        const bool tile_in = (flags & 2) != 0;
-        const uint32_t brick = brick_base + cur * brick_stride;
-        float* __restrict__ out = dst + (static_cast<int64_t>(z0) * oy + y0) * dpitch + x0 + thr_off;
-        float u0[3];
-#pragma unroll
-        for (int d = 0; d < 3; ++d) u0[d] = c0l[d] + t0[d];
-        mbar_wait(&bar[cur], (parity >> cur) & 1u);
-#pragma unroll
-        for (int c = 0; c < kBrCols; ++c) {
-          const int y = y0 + oth + c * kBrRowStep, x = x0 + lane;
-          if (x < ox && y < oy) {
-            const BrickCol cc{brick - bias_off, plane_b, row_b, out_plane, u0[0], u0[1], u0[2],
-                              mcol[0][0], mcol[1][0], mcol[2][0]};
-            uint32_t rest = tile_in
-                                ? brick_column_packed<T, false, false, kBrTZ, BOUNDARY>(cc, mid, half, out, nz)
-                                : brick_column_packed<T, true, false, kBrTZ, BOUNDARY>(cc, mid, half, out, nz);
-            // voxels near a decision edge, outside the source, or with non-finite taps: exact path
-            while (rest) {
-              const int k = __ffs(rest) - 1;
-              rest &= rest - 1;
-              const float kf = static_cast<float>(k);
-              const float dz = fabsf(__fmaf_rn(kf, mcol[0][0], u0[0]) - mid[0]);
-              const float dy = fabsf(__fmaf_rn(kf, mcol[1][0], u0[1]) - mid[1]);
-              const float dx = fabsf(__fmaf_rn(kf, mcol[2][0], u0[2]) - mid[2]);
-              const bool outside = dz > half[0] + 0.5f + kEdge || dy > half[1] + 0.5f + kEdge ||
-                                   dx > half[2] + 0.5f + kEdge;
-              const float v = outside ? 0.0f
-                                      : brick_sample_exact<T, 1, BOUNDARY, SCRUB>(
-                                            p, brick, b0[0], b0[1], b0[2], g.BZ, g.BY, g.BX, z0 + k, y, x);
-              st_global_cs(out + k * out_plane, v);
-            }
-          }
-          // the thread's next column: kBrRowStep output rows further
-#pragma unroll
-          for (int d = 0; d < 3; ++d) u0[d] += tstep[d];
-          out += col_step;
-        }
-      }
-    }
-    if (flags & 8) parity ^= 1u << cur;
-    __syncthreads();  // buffer cur and s_geo[cur] are free; s_geo[cur^1] is published
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
 template <typename T>
@@ -847,7 +725,6 @@ static bool brick_geometry_tz(const AffineParams& p, bool ly, int tz, int64_t ma
   if (ext[0] > 256 || ext[1] > 256 || BX > 256) return false;
   const int64_t bytes = static_cast<int64_t>(ext[0]) * ext[1] * BX * sizeof(T);
   if (bytes > max_bytes) return false;
-  g->TZ = tz;
   g->BZ = ext[0];
   g->BY = ext[1];
   g->BX = BX;
@@ -878,14 +755,9 @@ static bool brick_geometry(const AffineParams& p, bool ly, bool finite_taps, Bri
   // deep tiles when the output is deep enough to fill them and the brick still leaves 3 CTAs/SM
   // (3 x 74 KB + static shared memory < 227 KB); else 8-deep tiles, >= 3 CTAs/SM as well; larger
   // footprints use the gather path
-  static const bool deep_ok = [] {  // B2_BRICK_TZ=8 forces the shallow tiles (measurements)
-    const char* e = getenv("B2_BRICK_TZ");
-    return !(e && atoi(e) == kBrTZ);
-  }();
-  if (deep_ok && !ly && finite_taps && p.order == 1 && p.oz > kBrTZ &&
-      brick_geometry_tz<T>(p, ly, kBrTZMax, 74 * 1024, g, smem_bytes))
-    return true;
-  return brick_geometry_tz<T>(p, ly, kBrTZ, 72 * 1024, g, smem_bytes);
+  // tight 8-deep bricks: <= 56 KB keeps 4 CTAs/SM; larger footprints use the gather path
+  (void)finite_taps;
+  return brick_geometry_tz<T>(p, ly, kBrTZ, 56 * 1024, g, smem_bytes);
 }
 
 template <typename T, int ORDER, int BOUNDARY, bool SCRUB, bool LY>
@@ -915,94 +787,26 @@ static int launch_brick(const AffineParams& p, const BrickGeom& g, size_t smem_b
     return B2_ERR_UNSUPPORTED;
   }
   constexpr int kBrTY = LY ? kBrLanes : kBrOther, kBrTX = LY ? kBrOther : kBrLanes;
-  const int tiles_z = (p.oz + g.TZ - 1) / g.TZ;
+  const int tiles_z = (p.oz + kBrTZ - 1) / kBrTZ;
   const int tiles_y = (p.oy + kBrTY - 1) / kBrTY;
   const int tiles_x = (p.ox + kBrTX - 1) / kBrTX;
-  const int64_t tiles = static_cast<int64_t>(tiles_z) * tiles_y * tiles_x;
-  if (tiles > 2147483647LL) return affine_gather_launch(p, sizeof(T) == 2 ? B2_DTYPE_U16 : B2_DTYPE_F32, stream);
+  if (tiles_x > 65535 || tiles_y > 65535)
+    return affine_gather_launch(p, sizeof(T) == 2 ? B2_DTYPE_U16 : B2_DTYPE_F32, stream);
   auto kern = affine_brick_kernel<T, ORDER, BOUNDARY, SCRUB, LY>;
   B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                static_cast<int>(smem_bytes)));
   B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
                                cudaSharedmemCarveoutMaxShared));
-  kern<<<static_cast<unsigned>(tiles), kBrThreads, smem_bytes, stream>>>(map, p, g, tiles_z, tiles_x);
+  const dim3 grid(static_cast<unsigned>(tiles_z), static_cast<unsigned>(tiles_x),
+                  static_cast<unsigned>(tiles_y));
+  kern<<<grid, kBrThreads, smem_bytes, stream>>>(map, p, g);
   B2_CUDA(cudaGetLastError());
   count_launch();
   return B2_OK;
-}
-
-template <typename T, int BOUNDARY>
-static int launch_brick_pers(const AffineParams& p, const BrickGeom& g, cudaStream_t stream) {
-  EncodeTiledFn encode = get_encode_tiled();
-  if (!encode) {
-    set_error("cuTensorMapEncodeTiled not available from the driver");
-    return B2_ERR_NO_DEVICE;
-  }
-  CUtensorMap map;
-  const cuuint64_t gdim[3] = {static_cast<cuuint64_t>(p.sx), static_cast<cuuint64_t>(p.sy),
-                              static_cast<cuuint64_t>(p.sz)};
-  const cuuint64_t gstride[2] = {static_cast<cuuint64_t>(p.spitch) * sizeof(T),
-                                 static_cast<cuuint64_t>(p.spitch) * p.sy * sizeof(T)};
-  const cuuint32_t box[3] = {static_cast<cuuint32_t>(g.BX), static_cast<cuuint32_t>(g.BY),
-                             static_cast<cuuint32_t>(g.BZ)};
-  const cuuint32_t estride[3] = {1, 1, 1};
-  const CUtensorMapDataType dt =
-      sizeof(T) == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
-  CUresult r = encode(&map, dt, 3, const_cast<void*>(p.src), gdim, gstride, box, estride,
-                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled failed (CUresult %d) for affine source (%d,%d,%d)", (int)r,
-              p.sz, p.sy, p.sx);
-    return B2_ERR_UNSUPPORTED;
-  }
-  const int tiles_z = (p.oz + kBrTZ - 1) / kBrTZ;
-  const int tiles_y = (p.oy + kBrOther - 1) / kBrOther;
-  const int tiles_x = (p.ox + kBrLanes - 1) / kBrLanes;
-  const int64_t tiles = static_cast<int64_t>(tiles_z) * tiles_y * tiles_x;
-  if (tiles > 2000000000LL) return B2_ERR_UNSUPPORTED;
-  int sms = 148;
-  sm_count(&sms);
-  const size_t smem = 2 * ((static_cast<size_t>(g.bytes) + 127) / 128 * 128) + 256;
-  auto kern = affine_brick_pers_kernel<T, BOUNDARY>;
-  B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
-                               cudaSharedmemCarveoutMaxShared));
-  const unsigned grid = static_cast<unsigned>(std::min<int64_t>(tiles, 2LL * sms));
-  kern<<<grid, kBpThreads, smem, stream>>>(map, p, g, tiles_z, tiles_x, static_cast<int>(tiles));
-  B2_CUDA(cudaGetLastError());
-  count_launch();
-  return B2_OK;
-}
-
-// B2_BRICK_PERSISTENT=0 selects the one-tile-per-CTA kernel for the cases the persistent one covers
-static bool brick_persistent_enabled() {
-  static const bool on = [] {
-    const char* e = getenv("B2_BRICK_PERSISTENT");
-    return !(e && e[0] == '0');
-  }();
-  return on;
 }
 
 template <typename T, bool LY>
 static int brick_typed_ly(const AffineParams& p, cudaStream_t stream, bool* eligible) {
-  // (float32 sources; the uint16 instantiation of the persistent kernel spills under its register
-  // cap and stays on the one-tile-per-CTA kernel)
-  if (!LY && p.order == 1 && p.scrub && sizeof(T) == 4 && brick_persistent_enabled()) {
-    // production case: persistent double-buffered kernel, two tight 8-deep bricks per CTA and two
-    // CTAs per SM (2 x 2 x 55 KB + static shared memory < 227 KB)
-    BrickGeom g{};
-    size_t smem = 0;
-    if (reinterpret_cast<uintptr_t>(p.src) % 16 == 0 &&
-        (static_cast<int64_t>(p.spitch) * sizeof(T)) % 16 == 0 &&
-        brick_geometry_common(p, &g) &&
-        brick_geometry_tz<T>(p, false, kBrTZ, 55 * 1024, &g, &smem)) {
-      *eligible = true;
-      return p.boundary == B2_BOUNDARY_CONSTANT
-                 ? launch_brick_pers<T, B2_BOUNDARY_CONSTANT>(p, g, stream)
-                 : launch_brick_pers<T, B2_BOUNDARY_ITK>(p, g, stream);
-    }
-  }
   BrickGeom g{};
   size_t smem = 0;
   const bool scrub = p.scrub && sizeof(T) == 4;
