@@ -35,7 +35,7 @@ EXPORTS = (
     "b2_affine3d", "b2_deskew_pitched", "b2_affine3d_pitched", "b2_overhang_fill_workspace", "b2_overhang_fill", "b2h_deskew",
     "b2h_affine3d", "b2h_release", "b2_launch_count",
     "b2_flatfield_workspace", "b2_flatfield_u16", "b2h_flatfield_u16", "b2h_deskew_affine3d",
-    "b2_overhang_fill_ex", "b2_average_slices", "b2h_deskew_fill", "b2_spline3_workspace", "b2_affine3d_spline3", "b2h_affine3d_spline3",
+    "b2_debug_oob_count", "b2_debug_bounds_check_build", "b2_overhang_fill_ex", "b2_average_slices", "b2h_deskew_fill", "b2_spline3_workspace", "b2_affine3d_spline3", "b2h_affine3d_spline3",
 )
 
 
@@ -116,6 +116,8 @@ def lib() -> ctypes.CDLL:
                                                 ctypes.POINTER(_i64), _int, _int]
         handle.b2h_release.restype = _int
         handle.b2_launch_count.restype = ctypes.c_uint64
+        handle.b2_debug_oob_count.restype = ctypes.c_uint64
+        handle.b2_debug_bounds_check_build.restype = _int
         if handle.b2_abi_version() != ABI_VERSION:
             raise B2Error(f"ABI mismatch: library {handle.b2_abi_version()} != binding {ABI_VERSION}")
         _lib = handle

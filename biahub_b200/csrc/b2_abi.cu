@@ -87,6 +87,8 @@ int fill_device_ex(float* vol, int64_t z, int64_t y, int64_t x, int use_mean, fl
 int average_slices_device(const float* src, int64_t z, int64_t plane, int n, float* dst,
                           cudaStream_t stream);
 int host_release();
+unsigned long long brick_oob_count();
+unsigned long long deskew_oob_count();
 size_t flatfield_workspace_bytes(int64_t Y, int64_t X);
 int flatfield_begin(int64_t Y, int64_t X, void* ws, cudaStream_t stream);
 int flatfield_median(const void* src, int64_t Z, int64_t Y, int64_t X, void* ws, size_t ws_bytes,
@@ -301,6 +303,19 @@ int b2h_affine3d_spline3(const void* h_src, int src_dtype, int64_t sz, int64_t s
 }
 
 int b2h_release(void) { return b2::host_release(); }
+
+uint64_t b2_debug_oob_count(void) {
+  cudaDeviceSynchronize();
+  return b2::brick_oob_count() + b2::deskew_oob_count();
+}
+
+int b2_debug_bounds_check_build(void) {
+#ifdef B2_BOUNDS_CHECK
+  return 1;
+#else
+  return 0;
+#endif
+}
 
 uint64_t b2_launch_count(void) { return b2::g_launches.load(std::memory_order_relaxed); }
 

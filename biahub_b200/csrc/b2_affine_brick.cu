@@ -130,6 +130,7 @@ __device__ __noinline__ float brick_sample_exact(const AffineParams& p, uint32_t
     iy = min(max(iy - by0, 0), BY - 1) + by0;
     ix = min(max(ix - bx0, 0), BX - 1) + bx0;
     const uint32_t off = static_cast<uint32_t>(((iz - bz0) * BY + (iy - by0)) * BX + (ix - bx0));
+    B2_SMEM_CHECK(off, 0u, static_cast<uint32_t>(BZ * BY * BX));
     float v = brick_elem<T>(brick + off * static_cast<uint32_t>(sizeof(T)));
     if (SCRUB && sizeof(T) == 4) v = scrub_value(v);
     return v;
@@ -154,7 +155,8 @@ __device__ __forceinline__ void brick_put(float* o, float v) {
 }
 
 struct BrickCol {
-  uint32_t brick, plane_b, row_b;  // `brick` = brick base MINUS kBrBiasOff(plane_b, row_b, es), see below
+  uint32_t brick, plane_b, row_b;  // `brick` = brick base minus the magic-floor index biases (packed routine)
+  uint32_t lo, hi;                 // shared-memory extent of the brick (B2_BOUNDS_CHECK builds)
   int64_t out_plane;
   float u0z, u0y, u0x;  // brick-local coordinate of the column's first voxel
   float mz, my, mx;     // coordinate step per output plane (first column of the matrix)
@@ -207,6 +209,8 @@ __device__ __forceinline__ uint32_t brick_column_linear(const BrickCol& c, const
                          (static_cast<uint32_t>(__float_as_int(ty)) * c.row_b +
                           (static_cast<uint32_t>(__float_as_int(tx)) * es + abase));
     const uint32_t a10 = a00 + c.plane_b;
+    B2_SMEM_CHECK(a00, c.lo, c.hi);
+    B2_SMEM_CHECK(a10 + c.row_b + es, c.lo, c.hi);
     // lower plane: r0..r3 keep their value unless the cell changed
     brick_quad_if<T>(a00 != a_up, a00, a00 + c.row_b, r0, r1, r2, r3);
     const float v000 = r0, v001 = r1, v010 = r2, v011 = r3;
@@ -363,6 +367,8 @@ __device__ __forceinline__ void brick_columns_packed(const BrickCol (&c)[NC], co
                              (static_cast<uint32_t>(__float_as_int(ty)) * c[i].row_b +
                               (static_cast<uint32_t>(__float_as_int(tx)) * es + c[i].brick));
         const uint32_t a10 = a00 + c[i].plane_b;
+        B2_SMEM_CHECK(a00, c[i].lo, c[i].hi);
+        B2_SMEM_CHECK(a10 + c[i].row_b + es, c[i].lo, c[i].hi);
         float (&lo)[4] = (k & 1) ? qb[i] : qa[i];  // lower source plane of this voxel
         float (&up)[4] = (k & 1) ? qa[i] : qb[i];  // upper plane: loaded now, lower plane next step
         brick_quad_moved<T>(a00, a_up[i], c[i].row_b, lo[0], lo[1], lo[2], lo[3]);
@@ -574,8 +580,8 @@ __global__ void __launch_bounds__(kBrThreads, 4)
       BrickCol cc[kBrCols];
 #pragma unroll
       for (int c = 0; c < kBrCols; ++c)
-        cc[c] = BrickCol{biased, plane_b, row_b, out_plane, u0s[c][0], u0s[c][1], u0s[c][2],
-                         mcol[0][0], mcol[1][0], mcol[2][0]};
+        cc[c] = BrickCol{biased, plane_b, row_b, brick, brick + static_cast<uint32_t>(g.bytes), out_plane,
+                         u0s[c][0], u0s[c][1], u0s[c][2], mcol[0][0], mcol[1][0], mcol[2][0]};
       uint32_t rest[kBrCols];
       if (tile_in) {
         brick_columns_packed<T, false, LY, BOUNDARY, kBrCols>(cc, mid, half, outs, nz, rest);
@@ -588,8 +594,9 @@ __global__ void __launch_bounds__(kBrThreads, 4)
 #pragma unroll
       for (int c = 0; c < kBrCols; ++c) {
         if (!col_ok[c]) continue;
-        const BrickCol cc[1] = {BrickCol{biased, plane_b, row_b, out_plane, u0s[c][0], u0s[c][1],
-                                         u0s[c][2], mcol[0][0], mcol[1][0], mcol[2][0]}};
+        const BrickCol cc[1] = {BrickCol{biased, plane_b, row_b, brick,
+                                         brick + static_cast<uint32_t>(g.bytes), out_plane, u0s[c][0],
+                                         u0s[c][1], u0s[c][2], mcol[0][0], mcol[1][0], mcol[2][0]}};
         float* const o1[1] = {outs[c]};
         uint32_t rest[1];
         brick_columns_packed<T, true, LY, BOUNDARY, 1>(cc, mid, half, o1, nz, rest);
@@ -607,8 +614,8 @@ __global__ void __launch_bounds__(kBrThreads, 4)
     float* __restrict__ o = out;
     if (ORDER == 1 && nz == kBrTZ) {
       // ---- float32 taps that may be non-finite (scrub off): brick_column_linear
-      const BrickCol cc{brick, plane_b, row_b, out_plane, u0[0], u0[1], u0[2], mcol[0][0], mcol[1][0],
-                        mcol[2][0]};
+      const BrickCol cc{brick, plane_b, row_b, brick, brick + static_cast<uint32_t>(g.bytes), out_plane,
+                        u0[0], u0[1], u0[2], mcol[0][0], mcol[1][0], mcol[2][0]};
       const uint32_t rest = tile_in ? brick_column_linear<T, SCRUB, false, LY>(cc, mid, half, out)
                                     : brick_column_linear<T, SCRUB, true, LY>(cc, mid, half, out);
       finish_exact(c, rest);
@@ -640,6 +647,7 @@ __global__ void __launch_bounds__(kBrThreads, 4)
         const uint32_t a = brick + static_cast<uint32_t>(static_cast<int>(rz)) * plane_b +
                            static_cast<uint32_t>(static_cast<int>(ry)) * row_b +
                            static_cast<uint32_t>(static_cast<int>(rx)) * es;
+        B2_SMEM_CHECK(a, brick, brick + static_cast<uint32_t>(g.bytes));
         v = brick_elem<T>(a);
         if (SCRUB && sizeof(T) == 4) v = scrub_value(v);
       } else {
@@ -652,6 +660,8 @@ __global__ void __launch_bounds__(kBrThreads, 4)
             static_cast<uint32_t>(__float_as_int(ty) - 0x4B400000) * row_b +
             static_cast<uint32_t>(__float_as_int(tx) - 0x4B400000) * es;
         const uint32_t a01 = a00 + row_b, a10 = a00 + plane_b, a11 = a10 + row_b;
+        B2_SMEM_CHECK(a00, brick, brick + static_cast<uint32_t>(g.bytes));
+        B2_SMEM_CHECK(a11 + es, brick, brick + static_cast<uint32_t>(g.bytes));
         const float v000 = brick_elem<T>(a00), v001 = brick_elem<T>(a00 + es);
         const float v010 = brick_elem<T>(a01), v011 = brick_elem<T>(a01 + es);
         const float v100 = brick_elem<T>(a10), v101 = brick_elem<T>(a10 + es);
@@ -832,6 +842,8 @@ static int brick_typed(const AffineParams& p, cudaStream_t stream, bool* eligibl
   }
   return brick_typed_ly<T, false>(p, stream, eligible);
 }
+
+B2_OOB_GETTER(brick_oob_count)
 
 int affine_brick_launch(const AffineParams& p, int src_dtype, cudaStream_t stream, bool* eligible) {
   if (src_dtype == B2_DTYPE_U16) return brick_typed<uint16_t>(p, stream, eligible);

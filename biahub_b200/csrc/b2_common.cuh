@@ -36,6 +36,31 @@ int sm_count(int* out);
 // ---------------------------------------------------------------- device helpers
 #ifdef __CUDACC__
 
+// -DB2_BOUNDS_CHECK (python -m biahub_b200._build with B2_NVCC_EXTRA=-DB2_BOUNDS_CHECK): every
+// computed shared-memory tap address of the TMA kernels is compared with the extent of the brick it
+// must fall into; violations are counted per translation unit and summed by b2_debug_oob_count().
+// compute-sanitizer is closed on the B200 pool this was developed on, so this build is how
+// scripts/sanitize_cases.py checks the tight brick margins (profiles/r2_bounds_check.txt).
+#ifdef B2_BOUNDS_CHECK
+static __device__ unsigned long long g_b2_oob = 0ull;
+#define B2_SMEM_CHECK(addr, lo, hi)                                                  \
+  do {                                                                               \
+    if ((addr) < (lo) || (addr) >= (hi)) atomicAdd(&g_b2_oob, 1ull);                 \
+  } while (0)
+#define B2_OOB_GETTER(name)                                                          \
+  unsigned long long name() {                                                        \
+    unsigned long long v = 0;                                                        \
+    cudaMemcpyFromSymbol(&v, g_b2_oob, sizeof(v));                                   \
+    return v;                                                                        \
+  }
+#else
+#define B2_SMEM_CHECK(addr, lo, hi) \
+  do {                              \
+  } while (0)
+#define B2_OOB_GETTER(name) \
+  unsigned long long name() { return 0ull; }
+#endif
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

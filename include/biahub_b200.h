@@ -214,6 +214,12 @@ B2_API int b2h_flatfield_u16(const void* h_src, int64_t z, int64_t y, int64_t x,
 /* release the per-process pinned/device staging pools of the b2h_* calls */
 B2_API int b2h_release(void);
 
+/* Debug aid.  A library built with -DB2_BOUNDS_CHECK compares every computed shared-memory tap
+ * address of the TMA deskew / generic-affine kernels with the extent of its brick and counts the
+ * violations (current device; synchronises).  Release builds return 0 from both calls. */
+B2_API uint64_t b2_debug_oob_count(void);
+B2_API int b2_debug_bounds_check_build(void);
+
 /* number of kernels this library has launched in the calling process (all threads) */
 B2_API uint64_t b2_launch_count(void);
 

@@ -97,6 +97,36 @@ u16v = rng.integers(0, 65536, size=shape, dtype=np.uint16)
 check("brick X uint16", b2.affine_warp(cuda(u16v), c3 @ tilt, shape, order=1, boundary="itk", _path=_cabi.PATH_TMA),
       ao.affine_oracle_numpy(u16v, c3 @ tilt, shape, 1, "itk"), 1e-4 * 65535)
 
+# ---- tight brick margins under random generic matrices (TMA brick kernel, both lane variants) ---
+from scipy.spatial.transform import Rotation  # noqa: E402
+
+frng = np.random.default_rng(77)
+n_fuzz = 0
+for trial in range(48):
+    fshape = (int(frng.integers(9, 40)), int(frng.integers(33, 120)), 4 * int(frng.integers(12, 40)))
+    oshape = (int(frng.integers(9, 40)), int(frng.integers(33, 120)), int(frng.integers(40, 150)))
+    ang = frng.uniform(-10, 10, size=3)
+    if trial % 3 == 0:
+        ang[0] += 90.0          # in-plane quarter turn: the lanes-along-y variant
+    A = Rotation.from_euler("zyx", ang[::-1], degrees=True).as_matrix() @ np.diag(frng.uniform(0.8, 1.25, size=3))
+    Mf = np.eye(4)
+    Mf[:3, :3] = A
+    Mf[:3, 3] = (np.array(fshape) - 1) / 2 - A @ ((np.array(oshape) - 1) / 2) + frng.uniform(-3, 3, size=3)
+    fv = (frng.random(fshape, dtype=np.float32) * 4095).astype(np.float32)
+    order = int(trial % 2 == 0)
+    try:
+        got = b2.affine_warp(cuda(fv), Mf, oshape, order=order, boundary=("itk", "constant")[trial % 4 < 2],
+                             _path=_cabi.PATH_TMA)
+    except _cabi.B2Unsupported:
+        continue                # footprint too large for the brick kernel: gather path in production
+    want = ao.affine_oracle_numpy(fv, Mf, oshape, order, ("itk", "constant")[trial % 4 < 2])
+    if order == 0:
+        assert np.array_equal(got.cpu().numpy(), want), ("fuzz", trial)
+    else:
+        assert np.abs(got.cpu().numpy() - want).max() <= 1e-4 * 4095, ("fuzz", trial)
+    n_fuzz += 1
+done.append(f"{n_fuzz} random generic matrices through the TMA brick kernel")
+
 # ---- cubic spline (method="scipy") ----------------------------------------------------------
 sv = np.nan_to_num(vol, nan=0)
 check("spline3 f32", b2.spline_warp(cuda(sv), c3 @ tilt), ao.affine_oracle_spline3(sv, c3 @ tilt), 1e-4 * 4095)
@@ -123,6 +153,10 @@ check("b2h_deskew_affine3d", b2.deskew_then_register(u, Mm, mid.shape, ls_angle_
       ao.affine_oracle_numpy(mid, Mm, mid.shape, 1, "itk"), 1e-4 * 65535)
 torch.cuda.synchronize()
 _cabi.lib().b2h_release()
-print(f"sanitize_cases: {len(done)} cases ok, {_cabi.launch_count()} kernel launches")
+lib = _cabi.lib()
+print(f"sanitize_cases: {len(done)} cases ok, {_cabi.launch_count()} kernel launches; "
+      f"bounds-check build: {bool(lib.b2_debug_bounds_check_build())}, "
+      f"out-of-brick shared-memory addresses: {int(lib.b2_debug_oob_count())}")
+assert int(lib.b2_debug_oob_count()) == 0
 for name in done:
     print("  ok ", name)
