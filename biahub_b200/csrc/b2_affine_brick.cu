@@ -22,7 +22,8 @@ namespace b2 {
 // Tile depth along z.  (16-deep tiles — less z halo per output voxel, 3 CTAs/SM — and a persistent
 // double-buffered variant with a producer warp were built in round 2, are bit-compatible, and
 // measure the same 1.2 ms on the C3-sized volume as 8-deep tiles: the kernel is bound by the
-// per-warp dependency chain, not by brick traffic, the TMA wait or the issue rate; git history.)
+// per-warp dependency chain, not by brick traffic, the TMA wait or the issue rate; an L2 prefetch of
+// the tile one wave ahead (cp.async.bulk.prefetch.tensor) measured flat as well; git history.)
 constexpr int kBrTZ = 8;
 // In-plane tile: 16 (y) x 32 (x) with lanes along x; LY variant 32 (y) x 16 (x) with lanes along y
 // for matrices that map output y onto source x (90-degree in-plane rotations: with lanes along x
@@ -42,7 +43,6 @@ constexpr float kEdge = 2.0e-3f;
 constexpr float kMagic = 12582912.0f;  // 1.5 * 2^23: (v + kMagic) - kMagic rounds v to nearest
 
 struct BrickGeom {
-  int prefetch;    // > 0: L2-prefetch the brick of the tile that many CTAs ahead in launch order
   int BZ, BY, BX;  // brick extent (elements)
   int bytes;       // BZ*BY*BX*sizeof(T)
   // hull of a full tile relative to its origin voxel: sum of the negative / positive parts of
@@ -463,30 +463,6 @@ __global__ void __launch_bounds__(kBrThreads, 4)
       mbar_expect_tx(&bar, static_cast<uint32_t>(g.bytes));
       tma_load_3d(brick, &src_map, &bar, tb0[2], tb0[1], tb0[0]);
     }
-    // While this CTA's brick is in flight (a quarter of the resident warp time of this kernel is
-    // the wait for it: DRAM latency + 40 KB), pull the brick of the tile that will start when the
-    // CTAs now resident retire — `g.prefetch` CTAs further along the launch order — into L2, so
-    // that its owner waits for an L2 hit.  Same float64 geometry, no shared-memory destination.
-    if (g.prefetch > 0) {
-      const int64_t gx = gridDim.x, gy = gridDim.y;
-      const int64_t lin = blockIdx.x + gx * (blockIdx.y + gy * static_cast<int64_t>(blockIdx.z)) + g.prefetch;
-      if (lin < gx * gy * gridDim.z) {
-        const int pz0 = static_cast<int>(lin % gx) * kBrTZ;
-        const int px0 = static_cast<int>((lin / gx) % gy) * kBrTX;
-        const int py0 = static_cast<int>(lin / (gx * gy)) * kBrTY;
-        const double pzf = static_cast<double>(pz0 + p.cz), pyf = static_cast<double>(py0 + p.cy),
-                     pxf = static_cast<double>(px0 + p.cx);
-        int q0[3];
-        bool miss = false;
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-          const double c = coord_full(p.m + 4 * d, pzf, pyf, pxf);
-          q0[d] = __double2int_rd(c + (g.neg[d] - kBrGuard));
-          miss = miss || q0[d] >= n[d] + 1 || __double2int_rd(c + (g.pos[d] + kBrGuard)) <= -2;
-        }
-        if (!miss) tma_prefetch_3d(&src_map, q0[2] & ~(kVec - 1), q0[1], q0[0]);
-      }
-    }
   }
   __syncthreads();
   int b0[3];
@@ -832,20 +808,9 @@ static int launch_brick(const AffineParams& p, const BrickGeom& g, size_t smem_b
                                static_cast<int>(smem_bytes)));
   B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
                                cudaSharedmemCarveoutMaxShared));
-  // prefetch distance = the CTAs one wave holds (4 per SM); B2_BRICK_PREFETCH overrides (0 = off)
-  BrickGeom gl = g;
-  {
-    static const int env_pf = [] {
-      const char* e = getenv("B2_BRICK_PREFETCH");
-      return e ? atoi(e) : -1;
-    }();
-    int sms = 148;
-    sm_count(&sms);
-    gl.prefetch = env_pf >= 0 ? env_pf : 4 * sms;
-  }
   const dim3 grid(static_cast<unsigned>(tiles_z), static_cast<unsigned>(tiles_x),
                   static_cast<unsigned>(tiles_y));
-  kern<<<grid, kBrThreads, smem_bytes, stream>>>(map, p, gl);
+  kern<<<grid, kBrThreads, smem_bytes, stream>>>(map, p, g);
   B2_CUDA(cudaGetLastError());
   count_launch();
   return B2_OK;
