@@ -406,8 +406,11 @@ __device__ __forceinline__ void brick_columns_packed(const BrickCol (&c)[NC], co
     if (bad[i] != bad[i]) rest[i] = (1u << nz) - 1u;
 }
 
+#ifndef B2_BRICK_MINB
+#define B2_BRICK_MINB 4  // CTAs per SM the register allocation aims at (64 registers)
+#endif
 template <typename T, int ORDER, int BOUNDARY, bool SCRUB, bool LY>
-__global__ void __launch_bounds__(kBrThreads, 4)
+__global__ void __launch_bounds__(kBrThreads, B2_BRICK_MINB)
     affine_brick_kernel(const __grid_constant__ CUtensorMap src_map,
                         const __grid_constant__ AffineParams p,
                         const __grid_constant__ BrickGeom g) {
