@@ -574,6 +574,24 @@ __global__ void __launch_bounds__(kBrThreads, B2_BRICK_MINB)
     }
   };
   constexpr bool kPacked = ORDER == 1 && (SCRUB || sizeof(T) == 2);  // finite taps
+  // A tile that is not strictly inside by its hull (`tile_in`) still has warps whose columns are:
+  // coordinates are linear in k, so a column is strictly interior iff its two end voxels are
+  // (all kBrTZ of them — the brick always covers a full tile).  Decided per WARP (vote), so the
+  // unchecked routine is taken without divergence, e.g. by the whole first z layer of a volume
+  // whose z shift keeps its taps inside but closer than one voxel to plane 0.
+  bool warp_in = tile_in;
+  if (kPacked && !tile_in) {
+    bool mine = true;
+#pragma unroll
+    for (int c = 0; c < kBrCols; ++c)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const float ue = __fmaf_rn(static_cast<float>(kBrTZ - 1), mcol[d][0], u0s[c][d]);
+        mine = mine && fabsf(u0s[c][d] - mid[d]) <= half[d] - kEdge &&
+               fabsf(ue - mid[d]) <= half[d] - kEdge;
+      }
+    warp_in = __all_sync(0xffffffffu, mine);
+  }
   if (kPacked) {
     const uint32_t biased = brick - 0x4B400000u * (plane_b + row_b + es);  // magic-floor index biases
     bool all_ok = true;
@@ -587,7 +605,7 @@ __global__ void __launch_bounds__(kBrThreads, B2_BRICK_MINB)
         cc[c] = BrickCol{biased, plane_b, row_b, brick, brick + static_cast<uint32_t>(g.bytes), out_plane,
                          u0s[c][0], u0s[c][1], u0s[c][2], mcol[0][0], mcol[1][0], mcol[2][0]};
       uint32_t rest[kBrCols];
-      if (tile_in) {
+      if (warp_in) {
         brick_columns_packed<T, false, LY, BOUNDARY, kBrCols>(cc, mid, half, outs, nz, rest);
       } else {
         brick_columns_packed<T, true, LY, BOUNDARY, kBrCols>(cc, mid, half, outs, nz, rest);
