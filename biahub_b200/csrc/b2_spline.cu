@@ -11,9 +11,9 @@
 //     signal this cascade equals the symmetric exponential filter
 //       c[i] = g * sum_k z^|k| s[i+k] = g * (C+[i] + C-[i] - s[i]),   g = -6z / (1 - z^2),
 //     with C+[i] = s[i] + z C+[i-1] and C-[i] = s[i] + z C-[i+1] both running on the INPUT (the
-//     parallel form of the same transfer function).  z^32 = 5e-19, so a recursion started from
-//     zero 32 samples before the chunk is exact to double precision: every thread owns a chunk
-//     of 16 samples of one line and needs no carry from its neighbours — any axis, no scan.
+//     parallel form of the same transfer function).  z^20 = 4e-12, so a recursion started from
+//     zero 20 samples before the chunk is exact far below float32 resolution: every thread owns a
+//     chunk of 32 samples of one line and needs no carry from its neighbours — any axis, no scan.
 //  2. evaluation: c = M o (float64, scipy's op order), outside [0, n-1] -> 0, else the 4x4x4
 //     taps floor(c)-1 .. floor(c)+2, mirror-extended, weighted with scipy's cubic weights.
 //     Integer outputs use scipy's conversion (t > 0 ? t + 0.5 : 0, clamped, truncated).
@@ -28,8 +28,10 @@ namespace {
 
 constexpr double kPole = -0.26794919243112270647;  // sqrt(3) - 2
 constexpr double kGain = 1.7320508075688772935;    // -6 z / (1 - z^2) = sqrt(3)
-constexpr int kWarm = 32;
-constexpr int kChunk = 16;
+// z^20 = 3.6e-12: the zero-started recursions are exact to 4e-12 of the signal after 20 warm-up
+// samples (float32 output: 6e-8); 32-sample chunks read each sample 3.25 times (2 x (20 + 32) / 32)
+constexpr int kWarm = 20;
+constexpr int kChunk = 32;
 
 __device__ __forceinline__ int mirror_index(int j, int n) {
   if (j >= 0 && j < n) return j;
