@@ -779,17 +779,13 @@ static bool brick_geometry_common(const AffineParams& p, BrickGeom* g) {
 }
 
 template <typename T>
-static bool brick_geometry(const AffineParams& p, bool ly, bool finite_taps, BrickGeom* g,
-                           size_t* smem_bytes) {
+static bool brick_geometry(const AffineParams& p, bool ly, BrickGeom* g, size_t* smem_bytes) {
   if (reinterpret_cast<uintptr_t>(p.src) % 16 != 0) return false;
   if ((static_cast<int64_t>(p.spitch) * sizeof(T)) % 16 != 0) return false;
   if (!brick_geometry_common(p, g)) return false;
-  // deep tiles when the output is deep enough to fill them and the brick still leaves 3 CTAs/SM
-  // (3 x 74 KB + static shared memory < 227 KB); else 8-deep tiles, >= 3 CTAs/SM as well; larger
-  // footprints use the gather path
-  // tight 8-deep bricks: <= 56 KB keeps 4 CTAs/SM; larger footprints use the gather path
-  (void)finite_taps;
-  return brick_geometry_tz<T>(p, ly, kBrTZ, 56 * 1024, g, smem_bytes);
+  // tight 8-deep bricks: typically ~41 KB (4 CTAs/SM, register-limited); up to 72 KB still leaves
+  // 3 CTAs/SM; larger footprints (strong out-of-plane rotations or scalings) use the gather path
+  return brick_geometry_tz<T>(p, ly, kBrTZ, 72 * 1024, g, smem_bytes);
 }
 
 template <typename T, int ORDER, int BOUNDARY, bool SCRUB, bool LY>
@@ -842,7 +838,7 @@ static int brick_typed_ly(const AffineParams& p, cudaStream_t stream, bool* elig
   BrickGeom g{};
   size_t smem = 0;
   const bool scrub = p.scrub && sizeof(T) == 4;
-  *eligible = brick_geometry<T>(p, LY, scrub || sizeof(T) == 2, &g, &smem);
+  *eligible = brick_geometry<T>(p, LY, &g, &smem);
   if (!*eligible) return B2_ERR_UNSUPPORTED;
 #define B2_BR(ORD, BND)                                            \
   (scrub ? launch_brick<T, ORD, BND, true, LY>(p, g, smem, stream) \
