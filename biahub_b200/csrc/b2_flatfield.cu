@@ -9,11 +9,12 @@
 // one uint64 accumulator of sum(2 * pattern) in the caller's workspace.
 //
 // Two HBM-bound kernels:
-//  * flatfield_median_kernel: one thread owns 4 adjacent pixels (8-byte coalesced loads along x)
-//    and finds the k-th smallest of the Z samples of each by a 4 x 4-bit radix select: per pass
-//    a 16-bin histogram (uint16 counters in shared memory, 128 B per thread) of the samples that
-//    match the prefix found so far; a 5th pass (even Z only) finds the next order statistic.
-//    Every pass re-reads the column from L2/HBM: 5 * Z*Y*X*2 bytes.  Integer work, exact.
+//  * flatfield_median_kernel: one thread owns 2 adjacent pixels (4-byte coalesced loads along x)
+//    and finds the middle samples of each by a 2 x 8-bit radix select: a 256-bin histogram of the
+//    high bytes (uint16 counters in shared memory, 1 KB per thread, bank-conflict free), then one
+//    of the low bytes of the samples in the selected bin; the same sweep keeps the smallest
+//    sample above that bin, so the upper middle sample of an even Z needs no further pass.
+//    Two sweeps over the column: 2 * Z*Y*X*2 bytes, the second mostly from L2.  Integer work, exact.
 //  * flatfield_apply_kernel: exact float64 quotient without the division subroutine: r = RN(1/p)
 //    once per pixel, then q0 = v*r, rem = fma(-p, q0, v), q = fma(rem, r, q0) — the correctly
 //    rounded quotient for every uint16 v and every half-integer p (checked exhaustively against
@@ -22,6 +23,7 @@
 // mean(pattern): every partial sum of half-integers below 2^52 is exact, so the integer sum equals
 // numpy's pairwise float64 sum bit for bit (tests/test_flatfield_oracle.py).
 #include <algorithm>
+#include <cstdlib>
 #include <type_traits>
 
 #include "b2_common.cuh"
@@ -30,6 +32,8 @@ namespace b2 {
 
 constexpr int kFfThreads = 256;
 constexpr int kFfPix = 4;  // pixels per thread (one 8-byte load per plane)
+constexpr int kFfBatch = 4;      // apply kernel: planes loaded before the first quotient
+constexpr int kFfApplyPlanes = 16;  // apply kernel: planes per CTA (the reciprocals are per CTA)
 
 struct FlatfieldParams {
   const uint16_t* src;
@@ -42,163 +46,281 @@ struct FlatfieldParams {
   int z0, zn;                  // plane window of the apply kernel
 };
 
-// histogram counter of (bin, pixel j) of thread t: [(bin * kFfPix + j) * kFfThreads + t]
-__device__ __forceinline__ uint32_t ff_slot(uint32_t bin, uint32_t j, uint32_t t) {
-  return ((bin * kFfPix + j) * kFfThreads + t) * 2u;
+// ---------------------------------------------------------------------------------------------
+// median: two sweeps over the column (high byte, low byte), 256-bin histograms in shared memory
+// ---------------------------------------------------------------------------------------------
+constexpr int kFmThreads = 64;  // threads per CTA
+constexpr int kFmPix = 2;       // pixels per thread: one 4-byte load per plane
+// counter of (bin, pixel j) of thread t: the 16-bit half j of the 32-bit word [bin][t] — a warp's
+// 32 threads always hit 32 different banks, whatever bins their samples fall into.  Bin 256 takes
+// the samples the second sweep discards (no predicated shared-memory accesses in the loop).
+constexpr uint32_t kFmBinStride = kFmThreads * 4u;
+constexpr int kFmRing = 32;     // planes of the load ring (4 bytes per thread and plane)
+constexpr int kFmGroup = 8;     // planes per cp.async group
+constexpr int kFmHistBytes = 257 * kFmThreads * 4;
+constexpr int kFmSmemBytes = kFmHistBytes + kFmRing * kFmThreads * 4;  // 72.25 KB: three CTAs per SM
+
+__device__ __forceinline__ uint32_t fm_lds16(uint32_t a) {
+  unsigned short c;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(c) : "r"(a));
+  return c;
+}
+__device__ __forceinline__ uint32_t fm_lds32(uint32_t a) {
+  uint32_t c;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(c) : "r"(a));
+  return c;
+}
+__device__ __forceinline__ void fm_sts16(uint32_t a, uint32_t c) {
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"(static_cast<unsigned short>(c)));
 }
 
-__global__ void __launch_bounds__(kFfThreads)
+// the thread's two pixels of one plane packed in 32 bits (pixel 0 in the low half).  asm volatile:
+// the compiler must keep these loads where the source puts them, a whole batch ahead of their use
+// (as plain __ldg it sinks them below the shared-memory code of the previous batch to save
+// registers, and every batch then waits for DRAM: measured 35 % of the kernel)
+__device__ __forceinline__ uint32_t fm_ldg32(const uint16_t* q) {
+  uint32_t w;
+  asm volatile("ld.global.nc.b32 %0, [%1];" : "=r"(w) : "l"(q));
+  return w;
+}
+__device__ __forceinline__ uint32_t fm_ldg16(const uint16_t* q) {
+  unsigned short w;
+  asm volatile("ld.global.nc.u16 %0, [%1];" : "=h"(w) : "l"(q));
+  return w;
+}
+template <bool VEC>
+__device__ __forceinline__ uint32_t fm_load(const uint16_t* q, bool two) {
+  if (VEC) return fm_ldg32(q);
+  const uint32_t lo = fm_ldg16(q);
+  return lo | ((two ? fm_ldg16(q + 1) : lo) << 16);
+}
+
+// One sweep over the Z samples of the thread's two pixels.
+//  SECOND == false: histogram of the high bytes of all samples.
+//  SECOND == true : histogram of the low bytes of the samples whose high byte is the one the
+//                   first sweep selected (pre[j] = that byte << 8), the others go to bin 256;
+//                   TRACK also keeps min(sample - (pre + 256)) in unsigned arithmetic, i.e. the
+//                   smallest sample above the selected bin (the upper middle sample of an even Z
+//                   when it lies outside the bin).
+// Two consecutive planes are counted together: four independent shared-memory round trips per
+// thread instead of two, and when both samples of a pixel fall into one bin each store writes
+// count + 2 (the counter updates of one pixel are otherwise an ordered chain, 29 cycles per LDS).
+template <bool VEC, bool SECOND, bool TRACK>
+__device__ __forceinline__ void fm_sweep(const uint16_t* __restrict__ q, int64_t plane, int Z, bool two,
+                                         uint32_t hb, const uint32_t (&pre)[kFmPix],
+                                         uint32_t (&above)[kFmPix], uint32_t ring) {
+  auto slot = [&](uint32_t w, int j) -> uint32_t {
+    if (!SECOND) {
+      const uint32_t bin = j == 0 ? ((w >> 8) & 0xffu) : (w >> 24);
+      return hb + 2u * j + bin * kFmBinStride;
+    }
+    const uint32_t v = j == 0 ? (w & 0xffffu) : (w >> 16);
+    if (TRACK) above[j] = min(above[j], v - (pre[j] + 256u));
+    // v ^ pre < 256 exactly when the high byte matches, and is the low byte then
+    return hb + 2u * j + min(v ^ pre[j], 256u) * kFmBinStride;
+  };
+  auto bump2 = [&](uint32_t wa, uint32_t wb) {
+    uint32_t a[kFmPix], b[kFmPix], ca[kFmPix], cb[kFmPix];
+#pragma unroll
+    for (int j = 0; j < kFmPix; ++j) {
+      a[j] = slot(wa, j);
+      b[j] = slot(wb, j);
+    }
+#pragma unroll
+    for (int j = 0; j < kFmPix; ++j) {
+      ca[j] = fm_lds16(a[j]);
+      cb[j] = fm_lds16(b[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < kFmPix; ++j) {
+      const uint32_t inc = a[j] == b[j] ? 2u : 1u;
+      fm_sts16(a[j], ca[j] + inc);
+      fm_sts16(b[j], cb[j] + inc);
+    }
+  };
+  auto bump1 = [&](uint32_t w) {
+    uint32_t a[kFmPix], c[kFmPix];
+#pragma unroll
+    for (int j = 0; j < kFmPix; ++j) a[j] = slot(w, j);
+#pragma unroll
+    for (int j = 0; j < kFmPix; ++j) c[j] = fm_lds16(a[j]);
+#pragma unroll
+    for (int j = 0; j < kFmPix; ++j) fm_sts16(a[j], c[j] + 1u);
+  };
+  if (VEC) {
+    // Ring of kFmRing planes in shared memory, filled by cp.async in groups of kFmGroup planes,
+    // kFmRing - kFmGroup planes ahead of the counting.  Every thread copies and reads only its own
+    // 4 bytes of each plane, so cp.async.wait_group is all the synchronisation there is.  (Plain
+    // loads into a register double buffer do not work here: ptxas sinks them below the
+    // shared-memory code of the previous batch and every batch then waits for DRAM — with 64 KB
+    // of counters per CTA only six warps live on an SM to hide it.)
+    constexpr int kSlots = kFmRing / kFmGroup;
+    const int ng = Z / kFmGroup;
+    const uint16_t* src = q;  // next plane to issue
+    auto issue = [&](int slot, bool real) {
+      if (real) {
+#pragma unroll
+        for (int u = 0; u < kFmGroup; ++u) {
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(
+                           ring + static_cast<uint32_t>(slot * kFmGroup + u) * kFmBinStride),
+                       "l"(src)
+                       : "memory");
+          src += plane;
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+#pragma unroll
+    for (int g = 0; g < kSlots - 1; ++g) issue(g, g < ng);
+#pragma unroll 1
+    for (int g0 = 0; g0 < ng; g0 += kSlots) {
+#pragma unroll
+      for (int sl = 0; sl < kSlots; ++sl) {
+        const int g = g0 + sl;
+        if (g < ng) {
+          issue((sl + kSlots - 1) % kSlots, g + kSlots - 1 < ng);
+          asm volatile("cp.async.wait_group %0;" ::"n"(kSlots - 1) : "memory");
+          uint32_t w[kFmGroup];
+#pragma unroll
+          for (int u = 0; u < kFmGroup; ++u)
+            w[u] = fm_lds32(ring + static_cast<uint32_t>(sl * kFmGroup + u) * kFmBinStride);
+#pragma unroll
+          for (int u = 0; u < kFmGroup; u += 2) bump2(w[u], w[u + 1]);
+        }
+      }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll 1
+    for (int z = ng * kFmGroup; z < Z; ++z) bump1(fm_load<true>(q + z * plane, two));
+  } else {
+    // unaligned pixel pairs (odd plane size or odd window start): 2-byte loads, no ring
+    int z = 0;
+#pragma unroll 1
+    for (; z + 1 < Z; z += 2)
+      bump2(fm_load<false>(q + z * plane, two), fm_load<false>(q + (z + 1) * plane, two));
+    if (z < Z) bump1(fm_load<false>(q + z * plane, two));
+  }
+}
+
+// Two-level scan of the thread's 256 words: for each pixel the bin where the cumulative count
+// passes rank k[j] (bin, rank within the bin, samples in the bin).  Sums of 16 bins are formed for
+// both pixels at once (16-bit halves cannot carry: every sum is at most Z <= 65535); "how many
+// cumulative sums are <= k" and "k - the largest of them" (an unsigned minimum) need no branch.
+__device__ __forceinline__ void fm_scan(uint32_t hb, const int (&k)[kFmPix], uint32_t (&bin)[kFmPix],
+                                        int (&rank)[kFmPix], int (&here)[kFmPix]) {
+  uint32_t gs[16];
+#pragma unroll
+  for (uint32_t g = 0; g < 16u; ++g) {
+    uint32_t s = 0;
+#pragma unroll
+    for (uint32_t u = 0; u < 16u; ++u) s += fm_lds32(hb + (g * 16u + u) * kFmBinStride);
+    gs[g] = s;
+  }
+#pragma unroll
+  for (int j = 0; j < kFmPix; ++j) {
+    const uint32_t kj = static_cast<uint32_t>(k[j]);
+    uint32_t acc = 0, rem = kj, grp = 0;
+#pragma unroll
+    for (uint32_t g = 0; g < 16u; ++g) {
+      acc += j == 0 ? (gs[g] & 0xffffu) : (gs[g] >> 16);
+      rem = min(rem, kj - acc);
+      grp += acc <= kj ? 1u : 0u;
+    }
+    grp = min(grp, 15u);
+    const uint32_t base = hb + 2u * j + grp * 16u * kFmBinStride;
+    uint32_t acc2 = 0, rem2 = rem, b = 0;
+#pragma unroll
+    for (uint32_t u = 0; u < 16u; ++u) {
+      acc2 += fm_lds16(base + u * kFmBinStride);
+      rem2 = min(rem2, rem - acc2);
+      b += acc2 <= rem ? 1u : 0u;
+    }
+    b = min(b, 15u);
+    bin[j] = grp * 16u + b;
+    rank[j] = static_cast<int>(rem2);
+    here[j] = static_cast<int>(fm_lds16(base + b * kFmBinStride));
+  }
+}
+
+__global__ void __launch_bounds__(kFmThreads)
     flatfield_median_kernel(const __grid_constant__ FlatfieldParams p) {
-  __shared__ uint16_t hist[16 * kFfPix * kFfThreads];  // 32 KB
+  extern __shared__ __align__(16) uint32_t fm_hist[];  // [257][kFmThreads] counters, then the load ring
   __shared__ unsigned long long block_sum;
   const uint32_t t = threadIdx.x;
-  const uint32_t hbase = smem_u32(hist);
-  const int64_t pix = p.p0 + (static_cast<int64_t>(blockIdx.x) * kFfThreads + t) * kFfPix;
+  const uint32_t hb = smem_u32(fm_hist) + t * 4u;
   const int64_t pend = p.p0 + p.pn;
-  // vector path needs all 4 pixels in range and an 8-byte aligned column start in every plane
-  const bool vec = (pix + kFfPix <= pend) && ((p.P & 3) == 0) && ((pix & 3) == 0);
-  const int npx = pix >= pend ? 0 : static_cast<int>(pend - pix < kFfPix ? pend - pix : kFfPix);
+  const int64_t pix_own = p.p0 + (static_cast<int64_t>(blockIdx.x) * kFmThreads + t) * kFmPix;
+  const int npx = pix_own >= pend ? 0 : static_cast<int>(pend - pix_own < kFmPix ? pend - pix_own : kFmPix);
+  // every thread runs the whole kernel (the warp votes below need all lanes): threads past the
+  // window redo the last pixel and write nothing
+  const int64_t pix = npx > 0 ? pix_own : pend - 1;
+  const bool two = npx == kFmPix;
+  // 4-byte loads need both pixels and an even element offset in every plane; decided per warp
+  const bool vec =
+      __all_sync(0xffffffffu, two && ((p.P & 1) == 0) && ((pix & 1) == 0)) != 0;
   if (t == 0) block_sum = 0ull;
+  const uint16_t* q = p.src + pix;
+  const uint32_t ring = smem_u32(fm_hist) + kFmHistBytes + t * 4u;  // [kFmRing][kFmThreads]
+
+  auto clear = [&]() {
+#pragma unroll 16
+    for (uint32_t b = 0; b < 256u; ++b)
+      asm volatile("st.shared.u32 [%0], %1;" ::"r"(hb + b * kFmBinStride), "r"(0u));
+  };
 
   const int k1 = (p.Z - 1) >> 1;  // 0-based rank of the lower middle sample
   const bool even = (p.Z & 1) == 0;
-  uint32_t prefix[kFfPix] = {0, 0, 0, 0};  // bits found so far (high to low)
-  int krem[kFfPix] = {k1, k1, k1, k1};     // rank within the samples matching the prefix
-  int ceq[kFfPix] = {0, 0, 0, 0};          // after the last pass: samples equal to the median
+  const int kk[kFmPix] = {k1, k1};
+  uint32_t pre[kFmPix] = {0u, 0u}, above[kFmPix] = {0xffffffffu, 0xffffffffu};
+  uint32_t hi[kFmPix], lo[kFmPix];
+  int here[kFmPix], krem[kFmPix], rank[kFmPix];
 
-  // VEC: the thread's 4 pixels are one aligned 8-byte load per plane (CTA-interior, P % 4 == 0)
-  auto load4 = [&](auto vec_tag, int z, uint32_t (&v)[kFfPix]) {
-    const uint16_t* q = p.src + static_cast<int64_t>(z) * p.P + pix;
-    if (decltype(vec_tag)::value) {
-      const uint2 w = __ldg(reinterpret_cast<const uint2*>(q));
-      v[0] = w.x & 0xffffu; v[1] = w.x >> 16; v[2] = w.y & 0xffffu; v[3] = w.y >> 16;
-    } else {
+  // sweep 1: high bytes
+  clear();
+  if (vec)
+    fm_sweep<true, false, false>(q, p.P, p.Z, two, hb, pre, above, ring);
+  else
+    fm_sweep<false, false, false>(q, p.P, p.Z, two, hb, pre, above, ring);
+  fm_scan(hb, kk, hi, krem, here);
+  bool outside = false;  // the upper middle sample lies above the selected high-byte bin
 #pragma unroll
-      for (int j = 0; j < kFfPix; ++j) v[j] = j < npx ? __ldg(q + j) : 0u;
-    }
-  };
+  for (int j = 0; j < kFmPix; ++j) {
+    pre[j] = hi[j] << 8;
+    outside = outside || (even && krem[j] + 1 >= here[j]);
+  }
+  const bool track = __any_sync(0xffffffffu, outside) != 0;
 
-#pragma unroll 1
-  for (int pass = 0; pass < 4; ++pass) {
-    const int shift = 12 - 4 * pass;
-    // clear this thread's counters
-#pragma unroll
-    for (uint32_t b = 0; b < 16; ++b)
-#pragma unroll
-      for (uint32_t j = 0; j < kFfPix; ++j)
-        asm volatile("st.shared.u16 [%0], %1;" ::"r"(hbase + ff_slot(b, j, t)), "h"((unsigned short)0));
-    if (npx > 0) {
-      auto histogram_pass = [&](auto vec_tag) {
-      // kFfAhead planes are loaded before their counters are touched: the counter updates are an
-      // ordered chain of shared-memory round trips (two samples of a column may hit the same
-      // bin), so without this the kernel waits for one global load at a time per thread
-      // (measured: 25 % of the HBM bandwidth, 35 % of the issue slots)
-      constexpr int kFfAhead = 8;
-      for (int zb = 0; zb < p.Z; zb += kFfAhead) {
-        uint32_t vv[kFfAhead][kFfPix];
-#pragma unroll
-        for (int u = 0; u < kFfAhead; ++u) {
-          if (zb + u < p.Z) {
-            load4(vec_tag, zb + u, vv[u]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < kFfPix; ++j) vv[u][j] = 0u;
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < kFfAhead; ++u) {
-          if (zb + u >= p.Z) break;
-          uint32_t (&v)[kFfPix] = vv[u];
-          // the four pixels own separate counters: their four loads are issued before the four
-          // stores (pixel order ld, add, st, ld, ... would chain the shared-memory round trips)
-          uint32_t addr[kFfPix];
-          bool on[kFfPix];
-          unsigned short cnt[kFfPix];
-#pragma unroll
-          for (uint32_t j = 0; j < kFfPix; ++j) {
-            const uint32_t hi = pass == 0 ? 0u : (v[j] >> (shift + 4));
-            on[j] = hi == prefix[j];
-            addr[j] = hbase + ff_slot((v[j] >> shift) & 15u, j, t);
-          }
-#pragma unroll
-          for (uint32_t j = 0; j < kFfPix; ++j) {
-            cnt[j] = 0;
-            if (on[j]) asm volatile("ld.shared.u16 %0, [%1];" : "=h"(cnt[j]) : "r"(addr[j]));
-          }
-#pragma unroll
-          for (uint32_t j = 0; j < kFfPix; ++j) {
-            const unsigned short c = static_cast<unsigned short>(cnt[j] + 1);
-            if (on[j]) asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr[j]), "h"(c));
-          }
-        }
-      }
-      };
-      if (vec) {
-        histogram_pass(std::true_type{});
-      } else {
-        histogram_pass(std::false_type{});
-      }
-      // scan: the bin where the cumulative count passes the rank
-#pragma unroll
-      for (uint32_t j = 0; j < kFfPix; ++j) {
-        int acc = 0;
-        uint32_t bin = 15;
-        int below = 0, here = 0;
-        bool found = false;
-#pragma unroll
-        for (uint32_t b = 0; b < 16; ++b) {
-          unsigned short c;
-          asm volatile("ld.shared.u16 %0, [%1];" : "=h"(c) : "r"(hbase + ff_slot(b, j, t)));
-          if (!found && acc + static_cast<int>(c) > krem[j]) {
-            found = true;
-            bin = b;
-            below = acc;
-            here = c;
-          }
-          acc += c;
-        }
-        krem[j] -= below;
-        prefix[j] = (prefix[j] << 4) | bin;
-        ceq[j] = here;
-      }
-    }
+  // sweep 2: low bytes of the samples in the selected bin
+  clear();
+  if (vec) {
+    if (track)
+      fm_sweep<true, true, true>(q, p.P, p.Z, two, hb, pre, above, ring);
+    else
+      fm_sweep<true, true, false>(q, p.P, p.Z, two, hb, pre, above, ring);
+  } else {
+    if (track)
+      fm_sweep<false, true, true>(q, p.P, p.Z, two, hb, pre, above, ring);
+    else
+      fm_sweep<false, true, false>(q, p.P, p.Z, two, hb, pre, above, ring);
   }
+  fm_scan(hb, krem, lo, rank, here);
 
-  // m1 = prefix; samples <= m1 among ALL samples: (k1 - krem) below + ceq equal.  The upper middle
-  // sample (rank k1 + 1, even Z) equals m1 when krem + 1 < ceq, else it is the smallest sample > m1.
-  uint32_t m2[kFfPix];
-  bool need_next = false;
-#pragma unroll
-  for (int j = 0; j < kFfPix; ++j) {
-    m2[j] = prefix[j];
-    if (even && j < npx && krem[j] + 1 >= ceq[j]) {
-      m2[j] = 0xffffffffu;
-      need_next = true;
-    }
-  }
-  if (need_next) {
-    auto next_pass = [&](auto vec_tag) {
-#pragma unroll 8
-      for (int z = 0; z < p.Z; ++z) {
-        uint32_t v[kFfPix];
-        load4(vec_tag, z, v);
-#pragma unroll
-        for (int j = 0; j < kFfPix; ++j)
-          if (v[j] > prefix[j] && m2[j] != prefix[j]) m2[j] = min(m2[j], v[j]);
-      }
-    };
-    if (vec) {
-      next_pass(std::true_type{});
-    } else {
-      next_pass(std::false_type{});
-    }
-  }
   unsigned long long local = 0ull;
 #pragma unroll
-  for (int j = 0; j < kFfPix; ++j) {
+  for (int j = 0; j < kFmPix; ++j) {
+    const uint32_t m1 = pre[j] | lo[j];
+    uint32_t m2 = m1;
+    // upper middle sample (rank k1 + 1, even Z): the same value while the rank stays inside the
+    // low-byte bin, else the next occupied low-byte bin, else the smallest sample above the
+    // high-byte bin (tracked by the second sweep)
+    if (even && rank[j] + 1 >= here[j]) {
+      uint32_t b = lo[j] + 1u;
+      while (b < 256u && fm_lds16(hb + 2u * j + b * kFmBinStride) == 0u) ++b;
+      m2 = b < 256u ? (pre[j] | b) : above[j] + pre[j] + 256u;
+    }
     if (j < npx) {
-      const uint32_t s2 = prefix[j] + m2[j];  // 2 * median
-      p.pattern[pix + j] = 0.5f * static_cast<float>(s2);
+      const uint32_t s2 = m1 + m2;  // 2 * median
+      p.pattern[pix_own + j] = 0.5f * static_cast<float>(s2);
       local += s2;
     }
   }
@@ -247,17 +369,11 @@ __global__ void __launch_bounds__(kFfThreads)
   const int zb = p.z0 + blockIdx.y * planes_per_cta;
   const int ze = min(zb + planes_per_cta, p.z0 + p.zn);
   OUT* __restrict__ dst = static_cast<OUT*>(p.dst);
-#pragma unroll 2
-  for (int z = zb; z < ze; ++z) {
+  auto unpack = [](const uint2 w, uint32_t (&v)[kFfPix]) {
+    v[0] = w.x & 0xffffu; v[1] = w.x >> 16; v[2] = w.y & 0xffffu; v[3] = w.y >> 16;
+  };
+  auto emit = [&](int z, const uint32_t (&v)[kFfPix]) {
     const int64_t off = static_cast<int64_t>(z) * p.P + pix;
-    uint32_t v[kFfPix];
-    if (vec) {
-      const uint2 w = __ldg(reinterpret_cast<const uint2*>(p.src + off));
-      v[0] = w.x & 0xffffu; v[1] = w.x >> 16; v[2] = w.y & 0xffffu; v[3] = w.y >> 16;
-    } else {
-#pragma unroll
-      for (int j = 0; j < kFfPix; ++j) v[j] = j < npx ? __ldg(p.src + off + j) : 0u;
-    }
     double r[kFfPix];
 #pragma unroll
     for (int j = 0; j < kFfPix; ++j) r[j] = ff_value(v[j], pat[j], rcp[j], mean, plain[j]);
@@ -277,6 +393,35 @@ __global__ void __launch_bounds__(kFfThreads)
       for (int j = 0; j < kFfPix; ++j)
         if (j < npx) __stcs(o + j, r[j]);
     }
+  };
+  int z = zb;
+  if (vec) {
+    // kFfBatch planes of loads in flight per thread before the first quotient
+#pragma unroll 1
+    for (; z + kFfBatch <= ze; z += kFfBatch) {
+      uint2 w[kFfBatch];
+#pragma unroll
+      for (int u = 0; u < kFfBatch; ++u)
+        w[u] = __ldcs(reinterpret_cast<const uint2*>(p.src + static_cast<int64_t>(z + u) * p.P + pix));
+#pragma unroll
+      for (int u = 0; u < kFfBatch; ++u) {
+        uint32_t v[kFfPix];
+        unpack(w[u], v);
+        emit(z + u, v);
+      }
+    }
+  }
+#pragma unroll 1
+  for (; z < ze; ++z) {
+    const int64_t off = static_cast<int64_t>(z) * p.P + pix;
+    uint32_t v[kFfPix];
+    if (vec) {
+      unpack(__ldcs(reinterpret_cast<const uint2*>(p.src + off)), v);
+    } else {
+#pragma unroll
+      for (int j = 0; j < kFfPix; ++j) v[j] = j < npx ? __ldg(p.src + off + j) : 0u;
+    }
+    emit(z, v);
   }
 }
 
@@ -341,13 +486,17 @@ int flatfield_median(const void* src, int64_t Z, int64_t Y, int64_t X, void* ws,
   FlatfieldParams p = ff_params(src, Z, Y, X, nullptr, ws);
   p.p0 = p0;
   p.pn = pn;
-  const int64_t per_cta = static_cast<int64_t>(kFfThreads) * kFfPix;
+  const int64_t per_cta = static_cast<int64_t>(kFmThreads) * kFmPix;
   const int64_t grid = (pn + per_cta - 1) / per_cta;
   if (grid > 2147483647LL) {
     set_error("flatfield: plane too large");
     return B2_ERR_INVALID;
   }
-  flatfield_median_kernel<<<static_cast<unsigned>(grid), kFfThreads, 0, stream>>>(p);
+  B2_CUDA(cudaFuncSetAttribute(flatfield_median_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               kFmSmemBytes));
+  B2_CUDA(cudaFuncSetAttribute(flatfield_median_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                               cudaSharedmemCarveoutMaxShared));
+  flatfield_median_kernel<<<static_cast<unsigned>(grid), kFmThreads, kFmSmemBytes, stream>>>(p);
   B2_CUDA(cudaGetLastError());
   count_launch();
   return B2_OK;
@@ -378,13 +527,11 @@ int flatfield_apply(const void* src, int64_t Z, int64_t Y, int64_t X, void* dst,
   p.zn = static_cast<int>(zn);
   const int64_t per_cta = static_cast<int64_t>(kFfThreads) * kFfPix;
   const int64_t gx = (p.P + per_cta - 1) / per_cta;
-  int sms = 148;
-  sm_count(&sms);
-  // enough CTAs for a few waves; each CTA amortises its reciprocals over planes_per_cta planes
-  int64_t gy = (static_cast<int64_t>(sms) * 16 + gx - 1) / gx;
-  gy = std::max<int64_t>(1, std::min<int64_t>(gy, zn));
-  const int planes = static_cast<int>((zn + gy - 1) / gy);
-  gy = (zn + planes - 1) / planes;
+  // kFfApplyPlanes planes per CTA: the four reciprocals of a thread are amortised over 64 voxels
+  // and the grid is tens of waves deep (with a few hundred planes per CTA the grid was 4.05 waves
+  // of 4 CTAs per SM: a fifth, almost empty wave cost 20 % of the kernel)
+  const int planes = static_cast<int>(std::min<int64_t>(kFfApplyPlanes, zn));
+  const int64_t gy = (zn + planes - 1) / planes;
   if (gx > 2147483647LL || gy > 65535) {
     set_error("flatfield: grid too large");
     return B2_ERR_INVALID;

@@ -56,6 +56,46 @@ def test_matches_oracle_bit_for_bit(shape, kind):
     assert _same(got32, want32[0])
 
 
+@pytest.mark.parametrize("shape", [(2, 3, 5), (4, 7, 9), (6, 5, 64), (7, 3, 33), (40, 6, 130), (801, 2, 64),
+                                   (800, 3, 66)])
+def test_median_across_radix_bin_boundaries(shape):
+    """The median kernel selects the high byte first and the low byte second; the upper middle
+    sample of an even Z may sit in another low-byte bin or another high-byte bin.  Columns built
+    to hit each of those cases, at odd and even plane sizes (scalar and 4-byte loads)."""
+    rng = np.random.default_rng(sum(shape))
+    Z, Y, X = shape
+    data = np.empty(shape, np.uint16)
+    flat = data.reshape(Z, -1)
+    for p in range(flat.shape[1]):
+        kind = p % 8
+        if kind == 0:    # two values either side of a high-byte boundary, half and half
+            base = int(rng.integers(1, 255)) << 8
+            col = np.where(np.arange(Z) < (Z + 1) // 2, base - 1, base)
+        elif kind == 1:  # lower half in one high-byte bin, upper half far above
+            col = np.where(np.arange(Z) < Z // 2, rng.integers(0x0100, 0x01ff), rng.integers(0x7000, 0xffff))
+        elif kind == 2:  # constant
+            col = np.full(Z, rng.integers(0, 65536))
+        elif kind == 3:  # all samples in one high-byte bin, many ties
+            col = 0x1200 + rng.integers(0, 4, size=Z)
+        elif kind == 4:  # full range
+            col = rng.integers(0, 65536, size=Z)
+        elif kind == 5:  # extremes only
+            col = np.where(rng.random(Z) < 0.5, 0, 65535)
+        elif kind == 6:  # distinct consecutive values straddling a boundary
+            col = 0x3400 - Z // 2 + np.arange(Z)
+        else:            # low byte 0xff / 0x00 neighbours
+            col = np.where(rng.random(Z) < 0.5, 0x20ff, 0x2100 + rng.integers(0, 2, size=Z) * 0x100)
+        flat[:, p] = rng.permutation(np.asarray(col, dtype=np.int64)).astype(np.uint16)
+    with np.errstate(all="ignore"):
+        want64 = fo.flat_field_zyx_oracle(data)
+    assert _same(b2.flat_field_zyx(data), want64)
+    # the medians themselves (the pattern is what the kernel under test produces)
+    med = np.median(data, axis=0)
+    with np.errstate(all="ignore"):
+        want = data.astype(np.float64) / med * med.mean()
+    assert _same(want, want64)
+
+
 def test_reference_known_answer_and_passthrough():
     # reference tests/test_flat_field.py:76-90
     rng = np.random.default_rng(0)
