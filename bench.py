@@ -252,7 +252,7 @@ def kernel_name(w):
     return {"deskew": "deskew_tma_kernel",
             "chain": "deskew_tma_kernel + affine_zsep_kernel (bytes and time of both)",
             "flatfield": "flatfield_median_kernel + flatfield_apply_kernel (time of both; algorithmic bytes "
-                         "= one read + one write, the radix select re-reads the source)"}.get(
+                         "= one read + one write; the radix select makes two sweeps over the source)"}.get(
         w["kind"], "affine_brick_kernel" if w.get("generic") else "affine_zsep_kernel")
 
 

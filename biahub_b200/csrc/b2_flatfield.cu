@@ -49,14 +49,23 @@ struct FlatfieldParams {
 // ---------------------------------------------------------------------------------------------
 // median: two sweeps over the column (high byte, low byte), 256-bin histograms in shared memory
 // ---------------------------------------------------------------------------------------------
-constexpr int kFmThreads = 64;  // threads per CTA
+#ifndef B2_FM_THREADS
+#define B2_FM_THREADS 64
+#endif
+#ifndef B2_FM_RING
+#define B2_FM_RING 32
+#endif
+#ifndef B2_FM_GROUP
+#define B2_FM_GROUP 8
+#endif
+constexpr int kFmThreads = B2_FM_THREADS;  // threads per CTA
 constexpr int kFmPix = 2;       // pixels per thread: one 4-byte load per plane
 // counter of (bin, pixel j) of thread t: the 16-bit half j of the 32-bit word [bin][t] — a warp's
 // 32 threads always hit 32 different banks, whatever bins their samples fall into.  Bin 256 takes
 // the samples the second sweep discards (no predicated shared-memory accesses in the loop).
 constexpr uint32_t kFmBinStride = kFmThreads * 4u;
-constexpr int kFmRing = 32;     // planes of the load ring (4 bytes per thread and plane)
-constexpr int kFmGroup = 8;     // planes per cp.async group
+constexpr int kFmRing = B2_FM_RING;     // planes of the load ring (4 bytes per thread and plane)
+constexpr int kFmGroup = B2_FM_GROUP;     // planes per cp.async group
 constexpr int kFmHistBytes = 257 * kFmThreads * 4;
 constexpr int kFmSmemBytes = kFmHistBytes + kFmRing * kFmThreads * 4;  // 72.25 KB: three CTAs per SM
 
