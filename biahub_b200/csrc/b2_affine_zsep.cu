@@ -323,10 +323,19 @@ __global__ void __launch_bounds__(kZsThreads, 3)
       p_last[i] = v[i];
     }
   };
-  // LY store phase: thread t writes column t % 16 of the rows t / 16 + 16 j (64-byte row segments)
+  // LY store phase: thread t writes column t % 16 of the rows t / 16 + 16 j (64-byte row segments);
+  // the element offsets relative to the tile origin are formed once (-1 = no voxel), not per plane
   uint32_t oparity = 0;
+  constexpr int kStoreRows = kZsConsumers / kZsTileOther;   // rows written per pass
+  constexpr int kStoreIters = kZsTileLanes / kStoreRows;
   const int sc = tid % kZsTileOther, sr = tid / kZsTileOther;
-  const bool sc_ok = x0 + sc < p.ox;
+  int soff[kStoreIters];
+#pragma unroll
+  for (int j = 0; j < kStoreIters; ++j) {
+    const int r = sr + j * kStoreRows;
+    soff[j] = (LY && x0 + sc < p.ox && y0 + r < p.oy) ? r * p.dpitch + sc : -1;
+  }
+  const uint32_t sld = static_cast<uint32_t>((sr * kZsOutPitch + sc) * 4);
   auto store_plane = [&](const float (&o)[kZsPPT]) {
     if (LY) {
       // transpose through shared memory: lanes run along y here, the global rows run along x
@@ -337,13 +346,12 @@ __global__ void __launch_bounds__(kZsThreads, 3)
         asm volatile("st.shared.f32 [%0], %1;" ::"r"(buf + static_cast<uint32_t>(ooff[i])), "f"(o[i]));
       asm volatile("bar.sync 1, %0;" ::"n"(kZsConsumers) : "memory");  // consumers only
 #pragma unroll
-      for (int j = 0; j < kZsTileLanes / (kZsConsumers / kZsTileOther); ++j) {
-        const int r = sr + j * (kZsConsumers / kZsTileOther);
+      for (int j = 0; j < kStoreIters; ++j) {
         float v;
         asm volatile("ld.shared.f32 %0, [%1];"
                      : "=f"(v)
-                     : "r"(buf + static_cast<uint32_t>((r * kZsOutPitch + sc) * 4)));
-        if (sc_ok && y0 + r < p.oy) st_global_cs(out_tile + static_cast<int64_t>(r) * p.dpitch + sc, v);
+                     : "r"(buf + sld + static_cast<uint32_t>(j * kStoreRows * kZsOutPitch * 4)));
+        if (full_tile || soff[j] >= 0) st_global_cs(out_tile + soff[j], v);
       }
       return;
     }
@@ -439,8 +447,10 @@ static bool zsep_geometry(const AffineParams& p, bool ly, ZsepGeom* g, size_t* s
   const double ex = fabs(m[9]) * (kZsTY - 1) + fabs(m[10]) * (kZsTX - 1);
   if (!(ey < 240.0) || !(ex < 240.0)) return false;
   const int vec = 16 / sizeof(T);
-  const int BY = static_cast<int>(ey) + 5;
-  int BX = static_cast<int>(ex) + 5 + (vec - 1);  // + alignment slack of the brick origin
+  // rows by0 .. floor(max) + 2 with by0 = floor(min): at most floor(e) + 3 of them, and the kernel
+  // asks for (by_hi - by0) < BY
+  const int BY = static_cast<int>(ey) + 4;
+  int BX = static_cast<int>(ex) + 4 + (vec - 1);  // + alignment slack of the brick origin
   BX = (BX + vec - 1) / vec * vec;
   // (a bank-aligned row pitch was measured and makes no difference: the lanes of a warp span ~34
   // columns under a 1.07x scale, so every LDS costs 2 wavefronts either way and the kernel is not
