@@ -49,6 +49,7 @@ struct BrickGeom {
   // m_dj * (T_j - 1) per source axis d (host, float64)
   double neg[3], pos[3];
   float mcol[9];   // float32 copy of the 3x3 linear part (row-major) for the fp32 increments
+  float half[3];   // 0.5 * (n_d - 1) of the source axes: interior <=> |u - mid| <= half - edge
 };
 
 template <typename T>
@@ -391,14 +392,13 @@ __device__ __forceinline__ void brick_columns_packed(const BrickCol (&c)[NC], co
         // a NaN/inf tap makes v non-finite; the voxel is stored anyway and the whole column is
         // redone on the exact path (which applies the scrub per tap) after the loop
         if (sizeof(T) == 4) bad[i] = __fmaf_rn(v, 0.0f, bad[i]);
-        if (k < nz) brick_put<LY>(reinterpret_cast<float*>(o[i]), v);
+        if (k < nz) brick_put<LY>(reinterpret_cast<float*>(o[i] + k * plane_bytes), v);
       } else {
         if (k < nz) rest[i] |= 1u << k;
         a_up[i] = 0xffffffffu;
       }
       uz[i] += c[i].mz;
       uyx[i] = add2(uyx[i], myx[i]);
-      o[i] += plane_bytes;
     }
   }
 #pragma unroll
@@ -436,8 +436,9 @@ __global__ void __launch_bounds__(kBrThreads, B2_BRICK_MINB)
   //      |coordinate| < 1e9 over the whole output so the int conversions are defined).
   //      CTA-uniform, so ONE thread evaluates it (float64, ~170 instructions), issues the TMA
   //      load and publishes the result through shared memory.
-  // b0[3], bits(c0l[3]), flags (1 = brick ok, 2 = tile strictly interior, 4 = tile outside)
-  __shared__ int s_geo[8];
+  // b0[3], bits(c0l[3]), flags (1 = brick ok, 2 = tile strictly interior, 4 = tile outside),
+  // bits(mid[3]) = source centre in brick-local coordinates
+  __shared__ int s_geo[12];
   if (threadIdx.x == 0) {
     int tb0[3], tbhi[3];
     const double zf = static_cast<double>(z0 + p.cz), yf = static_cast<double>(y0 + p.cy),
@@ -466,6 +467,8 @@ __global__ void __launch_bounds__(kBrThreads, B2_BRICK_MINB)
       mbar_expect_tx(&bar, static_cast<uint32_t>(g.bytes));
       tma_load_3d(brick, &src_map, &bar, tb0[2], tb0[1], tb0[0]);
     }
+#pragma unroll
+    for (int d = 0; d < 3; ++d) s_geo[8 + d] = __float_as_int(g.half[d] - static_cast<float>(tb0[d]));
   }
   __syncthreads();
   int b0[3];
@@ -478,6 +481,20 @@ __global__ void __launch_bounds__(kBrThreads, B2_BRICK_MINB)
   const bool brick_ok = (s_geo[6] & 1) != 0;
   const bool tile_in = (s_geo[6] & 2) != 0;
   if (s_geo[6] & 4) {  // the whole tile maps outside the source: zeros, nothing to load
+    if (x0 + kBrTX <= p.ox && y0 + kBrTY <= p.oy && (p.dpitch & 3) == 0 &&
+        (reinterpret_cast<uintptr_t>(p.dst) & 15) == 0) {
+      // full tile, 16-byte aligned rows: one 16-byte store per 4 voxels, the row pointer advanced
+      // by additions (this path is 12 % of the tiles of a rotated volume)
+      constexpr int kQ = kBrTX / 4;  // 16-byte pieces per tile row
+      static_assert(kBrThreads % (kQ * kBrTY) == 0, "zero fill: whole planes per pass");
+      constexpr int kPlanesPerPass = kBrThreads / (kQ * kBrTY);
+      const int q = threadIdx.x % kQ, yy = (threadIdx.x / kQ) % kBrTY, k0 = threadIdx.x / (kQ * kBrTY);
+      const int64_t plane = static_cast<int64_t>(p.oy) * p.dpitch;
+      float* o = p.dst + (static_cast<int64_t>(z0 + k0) * p.oy + y0 + yy) * p.dpitch + x0 + 4 * q;
+      for (int k = k0; k < nz; k += kPlanesPerPass, o += kPlanesPerPass * plane)
+        st_global_cs4(o, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
+      return;
+    }
     for (int i = threadIdx.x; i < nz * kBrTY * kBrTX; i += kBrThreads) {
       const int xx = i % kBrTX, yy = (i / kBrTX) % kBrTY, k = i / (kBrTX * kBrTY);
       if (x0 + xx < p.ox && y0 + yy < p.oy)
@@ -505,15 +522,12 @@ __global__ void __launch_bounds__(kBrThreads, B2_BRICK_MINB)
   // interior  <=>  |u - mid| <= half - kEdge   (both taps valid, away from every volume edge)
   // outside   <=>  |u - mid| >  half + 0.5 + kEdge on some axis
   float mcol[3][3], mid[3], half[3];
-  {
-    const int n[3] = {p.sz, p.sy, p.sx};
 #pragma unroll
-    for (int d = 0; d < 3; ++d) {
+  for (int d = 0; d < 3; ++d) {
 #pragma unroll
-      for (int j = 0; j < 3; ++j) mcol[d][j] = g.mcol[3 * d + j];
-      half[d] = 0.5f * static_cast<float>(n[d] - 1);
-      mid[d] = half[d] - static_cast<float>(b0[d]);
-    }
+    for (int j = 0; j < 3; ++j) mcol[d][j] = g.mcol[3 * d + j];
+    half[d] = g.half[d];
+    mid[d] = __int_as_float(s_geo[8 + d]);
   }
   const uint32_t es = static_cast<uint32_t>(sizeof(T));
   const uint32_t row_b = static_cast<uint32_t>(g.BX) * es;
@@ -769,6 +783,9 @@ static bool brick_geometry_tz(const AffineParams& p, bool ly, int tz, int64_t ma
 // (keeps the device-side int conversions defined)
 static bool brick_geometry_common(const AffineParams& p, BrickGeom* g) {
   for (int i = 0; i < 9; ++i) g->mcol[i] = static_cast<float>(p.m[4 * (i / 3) + (i % 3)]);
+  g->half[0] = 0.5f * static_cast<float>(p.sz - 1);
+  g->half[1] = 0.5f * static_cast<float>(p.sy - 1);
+  g->half[2] = 0.5f * static_cast<float>(p.sx - 1);
   for (int d = 0; d < 3; ++d) {
     const double reach = fabs(p.m[4 * d]) * (p.oz + fabs((double)p.cz)) +
                          fabs(p.m[4 * d + 1]) * (p.oy + fabs((double)p.cy)) +
