@@ -50,6 +50,8 @@ struct BrickGeom {
   double neg[3], pos[3];
   float mcol[9];   // float32 copy of the 3x3 linear part (row-major) for the fp32 increments
   float half[3];   // 0.5 * (n_d - 1) of the source axes: interior <=> |u - mid| <= half - edge
+  long long out_plane;  // elements between output planes (oy * dpitch), formed once on the host
+  unsigned out_plane_bytes;  // the same in bytes (the launch admits only kBrTZ * this < 2^32)
 };
 
 template <typename T>
@@ -309,7 +311,7 @@ template <typename T, bool CHECK, bool LY, int BOUNDARY, int NC>
 __device__ __forceinline__ void brick_columns_packed(const BrickCol (&c)[NC], const float (&mid)[3],
                                                      const float (&half)[3],
                                                      float* const (&out)[NC], const int nz,
-                                                     uint32_t (&rest)[NC]) {
+                                                     uint32_t (&rest)[NC], const uint32_t plane_bytes) {
   constexpr uint32_t es = static_cast<uint32_t>(sizeof(T));
   float bad[NC];      // turns NaN as soon as one voxel of the column is non-finite (v * 0 accumulates)
   float qa[NC][4];    // lo halves: taps (y0,x0) (y0,x1) (y1,x0) (y1,x1) of one plane
@@ -331,7 +333,8 @@ __device__ __forceinline__ void brick_columns_packed(const BrickCol (&c)[NC], co
     o[i] = reinterpret_cast<char*>(out[i]);
   }
   const f32x2 magic2 = pk2(kMagic, kMagic);
-  const int64_t plane_bytes = c[0].out_plane * 4;
+  // plane_bytes: byte offset between output planes, formed on the host (the launch admits only
+  // outputs with kBrTZ * plane_bytes < 2^32): k * plane_bytes is one uniform multiply per store
 #pragma unroll
   for (int k = 0; k < kBrTZ; ++k) {
 #pragma unroll
@@ -392,7 +395,8 @@ __device__ __forceinline__ void brick_columns_packed(const BrickCol (&c)[NC], co
         // a NaN/inf tap makes v non-finite; the voxel is stored anyway and the whole column is
         // redone on the exact path (which applies the scrub per tap) after the loop
         if (sizeof(T) == 4) bad[i] = __fmaf_rn(v, 0.0f, bad[i]);
-        if (k < nz) brick_put<LY>(reinterpret_cast<float*>(o[i] + k * plane_bytes), v);
+        if (k < nz)
+          brick_put<LY>(reinterpret_cast<float*>(o[i] + static_cast<uint32_t>(k) * plane_bytes), v);
       } else {
         if (k < nz) rest[i] |= 1u << k;
         a_up[i] = 0xffffffffu;
@@ -537,7 +541,8 @@ __global__ void __launch_bounds__(kBrThreads, B2_BRICK_MINB)
   // output voxel (k, yy, xx) of the tile goes to out + k * out_plane: global memory, or the
   // staged tile in shared memory (LY)
   const int64_t out_plane = LY ? static_cast<int64_t>(kBrTY * kBrOutPitch)
-                               : static_cast<int64_t>(p.oy) * p.dpitch;
+                               : static_cast<int64_t>(g.out_plane);
+  const uint32_t out_plane_bytes = LY ? static_cast<uint32_t>(kBrTY * kBrOutPitch * 4) : g.out_plane_bytes;
   // the thread's kBrCols columns: (yy, xx), validity, brick-local start coordinate, output pointer
   bool col_ok[kBrCols];
   int col_y[kBrCols], col_x[kBrCols];
@@ -620,9 +625,9 @@ __global__ void __launch_bounds__(kBrThreads, B2_BRICK_MINB)
                          u0s[c][0], u0s[c][1], u0s[c][2], mcol[0][0], mcol[1][0], mcol[2][0]};
       uint32_t rest[kBrCols];
       if (warp_in) {
-        brick_columns_packed<T, false, LY, BOUNDARY, kBrCols>(cc, mid, half, outs, nz, rest);
+        brick_columns_packed<T, false, LY, BOUNDARY, kBrCols>(cc, mid, half, outs, nz, rest, out_plane_bytes);
       } else {
-        brick_columns_packed<T, true, LY, BOUNDARY, kBrCols>(cc, mid, half, outs, nz, rest);
+        brick_columns_packed<T, true, LY, BOUNDARY, kBrCols>(cc, mid, half, outs, nz, rest, out_plane_bytes);
       }
 #pragma unroll
       for (int c = 0; c < kBrCols; ++c) finish_exact(c, rest[c]);
@@ -635,7 +640,7 @@ __global__ void __launch_bounds__(kBrThreads, B2_BRICK_MINB)
                                          u0s[c][1], u0s[c][2], mcol[0][0], mcol[1][0], mcol[2][0]}};
         float* const o1[1] = {outs[c]};
         uint32_t rest[1];
-        brick_columns_packed<T, true, LY, BOUNDARY, 1>(cc, mid, half, o1, nz, rest);
+        brick_columns_packed<T, true, LY, BOUNDARY, 1>(cc, mid, half, o1, nz, rest, out_plane_bytes);
         finish_exact(c, rest[0]);
       }
     }
@@ -786,6 +791,8 @@ static bool brick_geometry_common(const AffineParams& p, BrickGeom* g) {
   g->half[0] = 0.5f * static_cast<float>(p.sz - 1);
   g->half[1] = 0.5f * static_cast<float>(p.sy - 1);
   g->half[2] = 0.5f * static_cast<float>(p.sx - 1);
+  g->out_plane = static_cast<long long>(p.oy) * p.dpitch;
+  g->out_plane_bytes = static_cast<unsigned>(g->out_plane * 4);
   for (int d = 0; d < 3; ++d) {
     const double reach = fabs(p.m[4 * d]) * (p.oz + fabs((double)p.cz)) +
                          fabs(p.m[4 * d + 1]) * (p.oy + fabs((double)p.cy)) +
@@ -835,7 +842,9 @@ static int launch_brick(const AffineParams& p, const BrickGeom& g, size_t smem_b
   const int tiles_z = (p.oz + kBrTZ - 1) / kBrTZ;
   const int tiles_y = (p.oy + kBrTY - 1) / kBrTY;
   const int tiles_x = (p.ox + kBrTX - 1) / kBrTX;
-  if (tiles_x > 65535 || tiles_y > 65535)
+  // the kernel forms k * (output plane bytes), k < kBrTZ, in 32 bits
+  const bool plane_fits = static_cast<int64_t>(p.oy) * p.dpitch * 4 * kBrTZ < (1LL << 32);
+  if (tiles_x > 65535 || tiles_y > 65535 || !plane_fits)
     return affine_gather_launch(p, sizeof(T) == 2 ? B2_DTYPE_U16 : B2_DTYPE_F32, stream);
   auto kern = affine_brick_kernel<T, ORDER, BOUNDARY, SCRUB, LY>;
   B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
