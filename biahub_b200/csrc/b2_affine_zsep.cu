@@ -33,6 +33,10 @@ constexpr int kZsTileOther = 16;  // tile extent along the other in-plane axis
 constexpr int kZsPPT = (kZsTileLanes * kZsTileOther) / 256;  // output points per consumer thread
 constexpr int kZsOutPitch = kZsTileOther + 1;  // LY: padded pitch of the transposed output tile
 constexpr int kZsConsumers = 256;
+#ifndef B2_ZSEP_LY_GROUP
+#define B2_ZSEP_LY_GROUP 8
+#endif
+constexpr int kZsLyGroup = B2_ZSEP_LY_GROUP;  // LY rasterisation: tile columns per group (1 = x-fastest)
 constexpr int kZsThreads = kZsConsumers + 32;  // + one producer warp
 constexpr int kZsMaxStages = 8;  // ring depth is chosen per launch (ZsepGeom::stages, 3..8)
 constexpr int kZsRowsPerPass = kZsConsumers / kZsTileLanes;
@@ -112,8 +116,21 @@ __global__ void __launch_bounds__(kZsThreads, 3)
     return e;
   };
   const int tid = threadIdx.x;
-  const int y0 = blockIdx.y * kZsTY;
-  const int x0 = blockIdx.x * kZsTX;
+  // LY: the CTAs of a wave are rasterised in groups of kZsLyGroup tile columns (x) by all tile
+  // rows (y).  Their source bricks then line up along source x (= output y) — contiguous segments
+  // of the same DRAM rows — while their output rows still form 16 * kZsLyGroup * 4-byte runs;
+  // with plain x-fastest order every concurrent brick row opens another DRAM page.
+  int tile_x = blockIdx.x, tile_y = blockIdx.y;
+  if (LY && kZsLyGroup > 1) {
+    const int lin = blockIdx.y * gridDim.x + blockIdx.x;
+    const int per_group = kZsLyGroup * gridDim.y;
+    const int grp = lin / per_group, within = lin - grp * per_group;
+    const int gsize = min(kZsLyGroup, static_cast<int>(gridDim.x) - grp * kZsLyGroup);
+    tile_y = within / gsize;
+    tile_x = grp * kZsLyGroup + (within - tile_y * gsize);
+  }
+  const int y0 = tile_y * kZsTY;
+  const int x0 = tile_x * kZsTX;
   const int zb = blockIdx.z * g.zchunk;
   const int ze = min(zb + g.zchunk, p.oz);
   const int nz = ze - zb;
