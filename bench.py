@@ -62,20 +62,20 @@ WORKLOADS = {
     # configs[0]
     "deskew_c1": dict(kind="deskew", shape=(256, 256, 512), dtype="uint16", units=16,
                       ls_angle_deg=30.0, px_to_scan_ratio=0.386, keep_overhang=False,
-                      average_n_slices=1, e2e_units=8, ncu_traffic=2.267e8,
+                      average_n_slices=1, e2e_units=8, ncu_traffic=2.273e8,
                       desc="C1 deskew uint16 (Z=256,Y=256,X=512) theta=30 px=0.386 N=1 crop; 16 distinct volumes"),
     # configs[2]
     "register_c3": dict(kind="register", shape=(120, 2048, 2048), dtype="float32", units=8,
-                        e2e_units=4, ncu_traffic=4.4056e9,
+                        e2e_units=4, ncu_traffic=4.3879e9,
                         desc="C3 register float32 (Z=120,Y=2048,X=2048) rot 7.3deg scale 1.07 shift (0.4,3.25,-11.5) order 1"),
     # C3 geometry with a NON z-separable matrix (small 3-D rotation about Y and X on top of C3):
     # what an ESTIMATED registration matrix looks like; exercises the generic kernel
     "register_generic": dict(kind="register", shape=(120, 2048, 2048), dtype="float32", units=8,
-                             e2e_units=4, generic=True, ncu_traffic=3.9370e9,
+                             e2e_units=4, generic=True, ncu_traffic=3.9289e9,
                              desc="C3 shape float32 (120,2048,2048), generic 3-D affine (C3 matrix + 0.5/0.3 deg out-of-plane rotations), order 1"),
     # configs[3]
     "stabilize_c4": dict(kind="stabilize", shape=(64, 2048, 2048), dtype="float32", units=16,
-                         e2e_units=8, ncu_traffic=2.1206e9,
+                         e2e_units=8, ncu_traffic=2.1203e9,
                          desc="C4 stabilize float32 (Z=64,Y=2048,X=2048) fractional XYZ translations"),
     # the pipeline stage before deskew (not part of BASELINE's metric; here for
     # its roofline line): median over Z + exact float64 divide, uint16 -> float32
