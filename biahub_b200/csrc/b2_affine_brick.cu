@@ -422,10 +422,13 @@ __global__ void __launch_bounds__(kBrThreads, B2_BRICK_MINB)
   __shared__ uint64_t bar;
   constexpr int kVec = 16 / static_cast<int>(sizeof(T));
   constexpr int kBrTY = LY ? kBrLanes : kBrOther, kBrTX = LY ? kBrOther : kBrLanes;
-  uint8_t* smem_al = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
-  const uint32_t brick = smem_u32(smem_al);
+  // 128-byte aligned brick, in shared-window addresses (no generic pointer arithmetic per thread)
+  const uint32_t smem_base = smem_u32(smem_raw);
+  const uint32_t brick = (smem_base + 127u) & ~127u;
   // LY: staged output tile [kBrTZ][kBrTY][kBrOutPitch] behind the brick
-  float* stage_out = reinterpret_cast<float*>(smem_al + ((g.bytes + 127) / 128) * 128);
+  float* stage_out =
+      LY ? reinterpret_cast<float*>(smem_raw + (brick - smem_base) + ((g.bytes + 127) / 128) * 128)
+         : nullptr;
 
   // z-fastest rasterisation: consecutive CTAs share z-halo planes
   // 3-D grid (z tiles, x tiles, y tiles): x is the fastest launch dimension, so the rasterisation
@@ -442,7 +445,7 @@ __global__ void __launch_bounds__(kBrThreads, B2_BRICK_MINB)
   //      load and publishes the result through shared memory.
   // b0[3], bits(c0l[3]), flags (1 = brick ok, 2 = tile strictly interior, 4 = tile outside),
   // bits(mid[3]) = source centre in brick-local coordinates
-  __shared__ int s_geo[12];
+  __shared__ __align__(16) int s_geo[12];
   if (threadIdx.x == 0) {
     int tb0[3], tbhi[3];
     const double zf = static_cast<double>(z0 + p.cz), yf = static_cast<double>(y0 + p.cy),
@@ -475,16 +478,17 @@ __global__ void __launch_bounds__(kBrThreads, B2_BRICK_MINB)
     for (int d = 0; d < 3; ++d) s_geo[8 + d] = __float_as_int(g.half[d] - static_cast<float>(tb0[d]));
   }
   __syncthreads();
-  int b0[3];
-  float c0l[3];  // tile-origin coordinate relative to the brick origin
-#pragma unroll
-  for (int d = 0; d < 3; ++d) {
-    b0[d] = s_geo[d];
-    c0l[d] = __int_as_float(s_geo[3 + d]);
-  }
-  const bool brick_ok = (s_geo[6] & 1) != 0;
-  const bool tile_in = (s_geo[6] & 2) != 0;
-  if (s_geo[6] & 4) {  // the whole tile maps outside the source: zeros, nothing to load
+  // three 16-byte loads instead of ten 4-byte ones
+  const int4 ga = *reinterpret_cast<const int4*>(s_geo);
+  const int4 gb = *reinterpret_cast<const int4*>(s_geo + 4);
+  const int4 gc = *reinterpret_cast<const int4*>(s_geo + 8);
+  const int b0[3] = {ga.x, ga.y, ga.z};
+  // tile-origin coordinate relative to the brick origin
+  const float c0l[3] = {__int_as_float(ga.w), __int_as_float(gb.x), __int_as_float(gb.y)};
+  const int geo_flags = gb.z;
+  const bool brick_ok = (geo_flags & 1) != 0;
+  const bool tile_in = (geo_flags & 2) != 0;
+  if (geo_flags & 4) {  // the whole tile maps outside the source: zeros, nothing to load
     if (x0 + kBrTX <= p.ox && y0 + kBrTY <= p.oy && (p.dpitch & 3) == 0 &&
         (reinterpret_cast<uintptr_t>(p.dst) & 15) == 0) {
       // full tile, 16-byte aligned rows: one 16-byte store per 4 voxels, the row pointer advanced
@@ -531,8 +535,10 @@ __global__ void __launch_bounds__(kBrThreads, B2_BRICK_MINB)
 #pragma unroll
     for (int j = 0; j < 3; ++j) mcol[d][j] = g.mcol[3 * d + j];
     half[d] = g.half[d];
-    mid[d] = __int_as_float(s_geo[8 + d]);
   }
+  mid[0] = __int_as_float(gc.x);
+  mid[1] = __int_as_float(gc.y);
+  mid[2] = __int_as_float(gc.z);
   const uint32_t es = static_cast<uint32_t>(sizeof(T));
   const uint32_t row_b = static_cast<uint32_t>(g.BX) * es;
   const uint32_t plane_b = static_cast<uint32_t>(g.BY) * row_b;
@@ -558,8 +564,11 @@ __global__ void __launch_bounds__(kBrThreads, B2_BRICK_MINB)
     for (int d = 0; d < 3; ++d)
       u0s[0][d] = __fmaf_rn(static_cast<float>(xx), mcol[d][2],
                             __fmaf_rn(static_cast<float>(yy), mcol[d][1], c0l[d]));
+    // global: CTA-uniform tile origin (uniform datapath) + a 32-bit offset inside the tile layer
     outs[0] = LY ? stage_out + yy * kBrOutPitch + xx
-                 : p.dst + (static_cast<int64_t>(z0) * p.oy + col_y[0]) * p.dpitch + col_x[0];
+                 : (p.dst + static_cast<int64_t>(z0) * g.out_plane +
+                    static_cast<int64_t>(y0) * p.dpitch + x0) +
+                       (yy * p.dpitch + xx);
     const int64_t ostep = LY ? static_cast<int64_t>(kBrRowStep)
                              : static_cast<int64_t>(kBrRowStep) * p.dpitch;
 #pragma unroll
