@@ -746,13 +746,32 @@ __global__ void __launch_bounds__(kBrThreads, B2_BRICK_MINB)
     }
   }
   if (LY) {
-    // staged tile -> global memory: lanes along x again (16 columns = 64-byte row segments)
+    // staged tile -> global memory: lanes along x again (16 columns = 64-byte row segments).
+    // Each thread owns 4 consecutive x of one row and every other plane; its global pointer is
+    // formed once and advanced by additions (the flat-index version of this loop — two integer
+    // divisions, a 64-bit index product and two bounds tests per element — was 16 % of the
+    // kernel's instructions).
     __syncthreads();
-    for (int i = threadIdx.x; i < nz * kBrTY * kBrTX; i += kBrThreads) {
-      const int xx = i % kBrTX, yy = (i / kBrTX) % kBrTY, k = i / (kBrTX * kBrTY);
-      if (x0 + xx < p.ox && y0 + yy < p.oy)
-        st_global_cs(p.dst + (static_cast<int64_t>(z0 + k) * p.oy + y0 + yy) * p.dpitch + x0 + xx,
-                     stage_out[(k * kBrTY + yy) * kBrOutPitch + xx]);
+    static_assert(kBrTX % 4 == 0 && kBrThreads % ((kBrTX / 4) * kBrTY) == 0, "LY copy-out mapping");
+    constexpr int kQ = kBrTX / 4;                             // 16-byte pieces per tile row
+    constexpr int kPlanesPerPass = kBrThreads / (kQ * kBrTY);  // planes written per pass
+    const int q = threadIdx.x % kQ, yy = (threadIdx.x / kQ) % kBrTY, k0 = threadIdx.x / (kQ * kBrTY);
+    const int xx = 4 * q;
+    const bool row_ok = y0 + yy < p.oy;
+    const bool vec_ok = row_ok && x0 + xx + 4 <= p.ox && (p.dpitch & 3) == 0 &&
+                        (reinterpret_cast<uintptr_t>(p.dst) & 15) == 0;
+    float* o = p.dst + static_cast<int64_t>(z0 + k0) * g.out_plane +
+               static_cast<int64_t>(y0 + yy) * p.dpitch + x0 + xx;
+    const float* st = stage_out + (k0 * kBrTY + yy) * kBrOutPitch + xx;
+    for (int k = k0; k < nz; k += kPlanesPerPass, o += kPlanesPerPass * g.out_plane,
+             st += kPlanesPerPass * kBrTY * kBrOutPitch) {
+      if (vec_ok) {
+        st_global_cs4(o, make_float4(st[0], st[1], st[2], st[3]));
+      } else if (row_ok) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (x0 + xx + j < p.ox) st_global_cs(o + j, st[j]);
+      }
     }
   }
 }

@@ -1,7 +1,6 @@
 #!/bin/bash
 cd /root/repo
 mkdir -p gpurun_out
-timeout 300 python scripts/ly_probe.py rot90 > gpurun_out/ly_probe_plain.log 2>&1 || { echo plain failed; tail gpurun_out/ly_probe_plain.log; exit 1; }
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:affine_zsep -s 2 -c 1 -f -o gpurun_out/prof_zsep_ly_rot90_new python scripts/ly_probe.py rot90 > gpurun_out/ly_probe_ncu.log 2>&1
-BIAHUB_B200_LIB=/root/repo/biahub_b200/_lib/variants/libb2_zsold.so timeout 600 ncu --set full --clock-control none --import-source on -k regex:affine_zsep -s 2 -c 1 -f -o gpurun_out/prof_zsep_ly_rot90_old python scripts/ly_probe.py rot90 > gpurun_out/ly_probe_ncu2.log 2>&1
-tail -2 gpurun_out/ly_probe_ncu2.log
+timeout 300 python scripts/ly_probe.py generic > gpurun_out/ly_probe_plain.log 2>&1 || { echo plain failed; tail gpurun_out/ly_probe_plain.log; exit 1; }
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:affine_brick -s 2 -c 1 -f -o gpurun_out/prof_brick_ly python scripts/ly_probe.py generic > gpurun_out/ly_probe_ncu.log 2>&1
+tail -2 gpurun_out/ly_probe_ncu.log
