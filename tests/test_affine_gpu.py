@@ -118,7 +118,7 @@ def test_unaligned_rows_not_tma_eligible():
     _compare(got, ao.affine_oracle_numpy(vol, MATRICES["generic"](vol.shape), vol.shape, 1, "itk"), 1)
 
 
-@pytest.mark.parametrize("mname", ["generic", "zflip", "fliplr_tilt", "big_tilt"])
+@pytest.mark.parametrize("mname", ["generic", "zflip", "fliplr_tilt", "big_tilt", "half_out"])
 def test_generic_brick_kernel(mname):
     """Non z-separable matrices take the 3-D TMA brick kernel (PATH_TMA raises otherwise): order 0
     bit-exact vs the float64 oracle, order 1 within tolerance, both boundary rules, uint16 too."""
@@ -132,6 +132,8 @@ def test_generic_brick_kernel(mname):
     th = np.radians(12.0)
     mats["big_tilt"] = lambda s: np.array([[np.cos(th), 0, -np.sin(th), 8.0], [0, 1, 0, -0.5],
                                            [np.sin(th), 0, np.cos(th), -3.0], [0, 0, 0, 1.0]])
+    # most tiles of the right half and of the top planes map outside the source: the zero-fill path
+    mats["half_out"] = lambda s: ao.translation_matrix_zyx((-9.0, 3.5, 110.25)) @ MATRICES["generic"](s)
     M = mats[mname](shape)
     out_shape = (30, 116, 204)
     vol = _vol(shape, seed=17, nan_frac=0.001)
@@ -365,17 +367,19 @@ def test_lanes_along_y_variant(mname):
     _compare(got, want, 1, name=f"{mname}/crop")
 
 
+@pytest.mark.parametrize("out_shape", [(21, 210, 141), (21, 210, 140), (24, 224, 160)])
 @pytest.mark.parametrize("order", [0, 1])
-def test_generic_lanes_along_y_variant(order):
+def test_generic_lanes_along_y_variant(order, out_shape):
     """Non z-separable matrix with a 90-degree in-plane part (an ESTIMATED registration on top of
-    the manual rotate90 approximation): brick kernel with lanes along y and staged stores."""
+    the manual rotate90 approximation): brick kernel with lanes along y and staged stores.
+    Output shapes: ragged with unaligned rows (scalar copy-out), ragged with 16-byte aligned rows
+    (16-byte copy-out and zero fill on the full tiles, scalar on the last x tile), whole tiles."""
     import torch
 
     import biahub_b200 as b2
     from biahub_b200 import _cabi, affine_warp
 
     shape = (20, 150, 204)
-    out_shape = (21, 210, 141)   # partial last z tile, ragged y / x tiles
     vol = _vol(shape, seed=33)
     c = (np.array(shape) - 1) / 2.0
     a, b = np.radians(1.5), np.radians(-0.8)
